@@ -1,0 +1,221 @@
+"""Deterministic synthetic weights and inputs (no checkpoints or datasets exist offline).
+
+The reference ships no weights in-tree and zero-initialises every AdaLN / output projection
+(/root/reference/lemas_tts/model/backbones/dit.py:171-181), which would make the DiT output
+identically zero and any parity test vacuous.  This factory therefore draws *every* tensor of
+the reference's checkpoint key layout (`transformer.*`, `accent_classifier.*`,
+optionally `prosody_*`) from a seeded CPU generator, with gains picked so activations stay O(1)
+through 22 blocks and the +-20 clamp of cfm.py:424 does not saturate.
+
+Used by tests, bench.py and the golden-vector generator.  CPU `torch.Generator` streams are
+bit-reproducible across machines, so fixtures minted in the build container and tensors made
+on the GPU box agree exactly.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+
+import torch
+
+
+@dataclass
+class DiTArch:
+    """Mirror of `model.arch` in configs/*.yaml plus the two ctor args load_model() adds."""
+
+    dim: int = 1024
+    depth: int = 22
+    heads: int = 16
+    dim_head: int = 64
+    ff_mult: int = 2
+    text_dim: int = 512
+    conv_layers: int = 4
+    mel_dim: int = 100
+    text_num_embeds: int = 898
+    text_mask_padding: bool = True
+    qk_norm: str | None = None
+    pe_attn_head: int | None = None
+    use_prosody_encoder: bool = False
+
+    def to_kwargs(self) -> dict:
+        return asdict(self)
+
+
+FULL_ARCH = DiTArch()
+# Reduced architecture for fast CPU oracle runs; same kernels (dim_head=64, dims multiple of 64).
+TINY_ARCH = DiTArch(dim=256, depth=2, heads=4, ff_mult=2, text_dim=128, conv_layers=2, text_num_embeds=60)
+
+
+def _gen(seed: int) -> torch.Generator:
+    return torch.Generator().manual_seed(int(seed))
+
+
+def _normal(g, shape, std):
+    return torch.randn(*shape, generator=g, dtype=torch.float32) * std
+
+
+def _linear(sd, g, name, n_out, n_in, gain=1.0, bias_std=0.02):
+    sd[f"{name}.weight"] = _normal(g, (n_out, n_in), gain / math.sqrt(n_in))
+    sd[f"{name}.bias"] = _normal(g, (n_out,), bias_std)
+
+
+def make_dit_state_dict(arch: DiTArch = FULL_ARCH, seed: int = 0) -> dict[str, torch.Tensor]:
+    """State dict in the reference key layout (what `load_checkpoint` strict-loads into CFM)."""
+    g = _gen(seed)
+    sd: dict[str, torch.Tensor] = {}
+    D, Dt, M = arch.dim, arch.text_dim, arch.mel_dim
+    inner = arch.heads * arch.dim_head
+    F = D * arch.ff_mult
+    p = "transformer."
+
+    _linear(sd, g, p + "time_embed.time_mlp.0", D, 256)
+    _linear(sd, g, p + "time_embed.time_mlp.2", D, D)
+
+    sd[p + "text_embed.text_embed.weight"] = _normal(g, (arch.text_num_embeds + 1, Dt), 1.0)
+    for i in range(arch.conv_layers):
+        q = f"{p}text_embed.text_blocks.{i}."
+        sd[q + "dwconv.weight"] = _normal(g, (Dt, 1, 7), 1.0 / math.sqrt(7))
+        sd[q + "dwconv.bias"] = _normal(g, (Dt,), 0.02)
+        sd[q + "norm.weight"] = 1.0 + _normal(g, (Dt,), 0.1)
+        sd[q + "norm.bias"] = _normal(g, (Dt,), 0.05)
+        _linear(sd, g, q + "pwconv1", 2 * Dt, Dt)
+        sd[q + "grn.gamma"] = _normal(g, (1, 1, 2 * Dt), 0.2)
+        sd[q + "grn.beta"] = _normal(g, (1, 1, 2 * Dt), 0.05)
+        _linear(sd, g, q + "pwconv2", Dt, 2 * Dt, gain=0.5)
+
+    if arch.use_prosody_encoder:
+        _linear(sd, g, p + "prosody_text_proj", Dt, 512)
+
+    _linear(sd, g, p + "input_embed.proj", D, 2 * M + Dt, gain=0.7)
+    for j in (0, 2):
+        q = f"{p}input_embed.conv_pos_embed.conv1d.{j}."
+        sd[q + "weight"] = _normal(g, (D, D // 16, 31), 1.0 / math.sqrt(31 * D // 16))
+        sd[q + "bias"] = _normal(g, (D,), 0.02)
+
+    sd[p + "rotary_embed.inv_freq"] = 1.0 / (
+        10000.0 ** (torch.arange(0, arch.dim_head, 2).float() / arch.dim_head)
+    )
+
+    for i in range(arch.depth):
+        q = f"{p}transformer_blocks.{i}."
+        # AdaLN-zero linear: small but non-zero so gates/scales/shifts are exercised.
+        _linear(sd, g, q + "attn_norm.linear", 6 * D, D, gain=0.35, bias_std=0.05)
+        _linear(sd, g, q + "attn.to_q", inner, D)
+        _linear(sd, g, q + "attn.to_k", inner, D)
+        _linear(sd, g, q + "attn.to_v", inner, D)
+        _linear(sd, g, q + "attn.to_out.0", D, inner)
+        _linear(sd, g, q + "ff.ff.0.0", F, D)
+        _linear(sd, g, q + "ff.ff.2", D, F)
+        if arch.qk_norm == "rms_norm":
+            sd[q + "attn.q_norm.weight"] = 1.0 + _normal(g, (arch.dim_head,), 0.1)
+            sd[q + "attn.k_norm.weight"] = 1.0 + _normal(g, (arch.dim_head,), 0.1)
+
+    _linear(sd, g, p + "norm_out.linear", 2 * D, D, gain=0.35, bias_std=0.05)
+    _linear(sd, g, p + "proj_out", M, D, gain=1.0)
+
+    # training-only head; present in every released checkpoint, so kept in the key set
+    _linear(sd, g, "accent_classifier.net.0", D, M)
+    _linear(sd, g, "accent_classifier.net.3", 12, D)
+    if arch.use_prosody_encoder:
+        _linear(sd, g, "prosody_to_mel", M, 512, gain=0.3)
+    return sd
+
+
+@dataclass
+class VocosArch:
+    """charactr/vocos-mel-24khz hyper-parameters (config.yaml of the pip package `vocos`)."""
+
+    input_channels: int = 100
+    dim: int = 512
+    intermediate_dim: int = 1536
+    num_layers: int = 8
+    n_fft: int = 1024
+    hop_length: int = 256
+
+
+FULL_VOCOS = VocosArch()
+TINY_VOCOS = VocosArch(dim=128, intermediate_dim=256, num_layers=2)
+
+
+def make_vocos_state_dict(arch: VocosArch = FULL_VOCOS, seed: int = 7) -> dict[str, torch.Tensor]:
+    """State dict in the `pytorch_model.bin` key layout of vocos-mel-24khz (backbone.* / head.*)."""
+    g = _gen(seed)
+    sd: dict[str, torch.Tensor] = {}
+    C, D, H = arch.input_channels, arch.dim, arch.intermediate_dim
+    sd["backbone.embed.weight"] = _normal(g, (D, C, 7), 1.0 / math.sqrt(7 * C))
+    sd["backbone.embed.bias"] = _normal(g, (D,), 0.02)
+    sd["backbone.norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+    sd["backbone.norm.bias"] = _normal(g, (D,), 0.05)
+    for i in range(arch.num_layers):
+        q = f"backbone.convnext.{i}."
+        sd[q + "dwconv.weight"] = _normal(g, (D, 1, 7), 1.0 / math.sqrt(7))
+        sd[q + "dwconv.bias"] = _normal(g, (D,), 0.02)
+        sd[q + "norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+        sd[q + "norm.bias"] = _normal(g, (D,), 0.05)
+        _linear(sd, g, q + "pwconv1", H, D)
+        _linear(sd, g, q + "pwconv2", D, H)
+        sd[q + "gamma"] = 0.25 + _normal(g, (D,), 0.05)
+    sd["backbone.final_layer_norm.weight"] = 1.0 + _normal(g, (D,), 0.1)
+    sd["backbone.final_layer_norm.bias"] = _normal(g, (D,), 0.05)
+    # log-magnitude half kept small so exp() stays well below the clip at 1e2 for most bins
+    _linear(sd, g, "head.out", arch.n_fft + 2, D, gain=0.5)
+    sd["head.istft.window"] = torch.hann_window(arch.n_fft)
+    return sd
+
+
+# ----------------------------------------------------------------------------- inputs
+
+
+def synthetic_ref_mel(batch: int, frames: int, n_mels: int = 100, seed: int = 0) -> torch.Tensor:
+    """log-mel-like reference: clamp(N(-4, 2^2), min=ln 1e-5)  (SURVEY.md §8d)."""
+    g = _gen(1000 + seed)
+    mel = torch.randn(batch, frames, n_mels, generator=g) * 2.0 - 4.0
+    return mel.clamp_(min=math.log(1e-5))
+
+
+def synthetic_ref_audio(batch: int, samples: int, seed: int = 0) -> torch.Tensor:
+    g = _gen(2000 + seed)
+    return 0.1 * torch.randn(batch, samples, generator=g)
+
+
+def synthetic_text_ids(batch: int, n_tokens: int, vocab: int = 898, seed: int = 0,
+                       lengths: list[int] | None = None) -> torch.Tensor:
+    """Token ids uniform in [0, vocab); rows shorter than n_tokens are padded with -1."""
+    g = _gen(3000 + seed)
+    ids = torch.randint(0, vocab, (batch, n_tokens), generator=g, dtype=torch.long)
+    if lengths is not None:
+        for b, n in enumerate(lengths):
+            ids[b, n:] = -1
+    return ids
+
+
+def synthetic_noise(durations: list[int], n_mels: int = 100, seed: int = 0) -> torch.Tensor:
+    """y0 as CFM.sample builds it (cfm.py:430-435): per-row randn(dur, n_mels), zero padded."""
+    g = _gen(4000 + seed)
+    n = max(durations)
+    y0 = torch.zeros(len(durations), n, n_mels)
+    for b, d in enumerate(durations):
+        y0[b, :d] = torch.randn(d, n_mels, generator=g)
+    return y0
+
+
+@dataclass
+class BenchConfig:
+    name: str
+    batch: int
+    ref_frames: int
+    total_frames: int  # N
+    n_text: int
+    steps: int
+    cfg_strength: float
+    sway_coef: float | None
+    seed: int
+
+
+# BASELINE.json configs made concrete.  C3's ragged shapes are drawn in bench/tests.
+CONFIGS = {
+    "C1": BenchConfig("C1", 1, 376, 940, 150, 16, 2.0, 5.0, 0),
+    "C2": BenchConfig("C2", 1, 937, 2187, 350, 32, 2.0, 5.0, 0),
+    "C4": BenchConfig("C4", 256, 256, 768, 120, 32, 2.0, 3.0, 2),
+    "C5": BenchConfig("C5", 1, 2813, 2814, 450, 64, 5.0, 3.0, 3),
+}

@@ -1,0 +1,39 @@
+"""Re-derive the inputs of the committed golden cases (tests/golden/MANIFEST.json) from their seeds."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import torch
+
+from lemas_tts import synthetic as syn
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+MANIFEST = json.loads((GOLDEN / "MANIFEST.json").read_text())
+CASES = {c["name"]: c for c in MANIFEST["cases"]}
+
+
+def load(name: str) -> dict:
+    return torch.load(GOLDEN / f"{name}.pt", weights_only=True)
+
+
+def inputs(case: dict):
+    """Same derivation as oracle/gen_golden.py:case_inputs (checked through `in_sums`)."""
+    arch = getattr(syn, case["arch"])
+    B, Tc, N = case["batch"], case["ref_frames"], case["frames"]
+    cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
+    if case.get("lens"):
+        for b, l in enumerate(case["lens"]):
+            cond[b, l:] = 0.0
+    text = syn.synthetic_text_ids(B, case["n_text"], arch.text_num_embeds, seed=case["seed"],
+                                  lengths=case.get("text_lens"))
+    durations = case.get("durations") or [N] * B
+    noise = syn.synthetic_noise(durations, arch.mel_dim, seed=case["seed"])
+    lens = torch.tensor(case["lens"]) if case.get("lens") else None
+    duration = torch.tensor(durations) if B > 1 else durations[0]
+    edit_mask = None
+    if case.get("edit"):
+        edit_mask = torch.ones(1, Tc, dtype=torch.bool)
+        edit_mask[:, case["edit"][0]: case["edit"][1]] = False
+    return dict(arch=arch, cond=cond, text=text, durations=durations, noise=noise, lens=lens,
+                duration=duration, edit_mask=edit_mask)

@@ -1,0 +1,80 @@
+"""Pins the CPU oracle (oracle/lemas_oracle.py) to golden vectors minted from the VERBATIM reference.
+
+Generator: oracle/gen_golden.py (imports /root/reference/lemas_tts/model/{cfm,modules,backbones/dit}.py).
+Bar: fp32 CPU vs fp32 CPU, same op order up to the restated split of third-party pieces -> 2e-5 abs.
+"""
+import pytest
+import torch
+
+import golden_cases as gc
+from lemas_tts import synthetic as syn
+from oracle import lemas_oracle as orc
+
+TOL = 2e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _threads():
+    torch.set_num_threads(8)
+
+
+@pytest.mark.parametrize("name", list(gc.CASES))
+def test_sample_matches_reference(name):
+    case = gc.CASES[name]
+    gold = gc.load(name)
+    inp = gc.inputs(case)
+    sums = torch.tensor([inp["cond"].double().abs().sum(), inp["noise"].double().abs().sum(),
+                         float(inp["text"].sum())], dtype=torch.float64)
+    assert torch.allclose(sums, gold["in_sums"], rtol=0, atol=1e-6), "synthetic inputs drifted from the fixture"
+
+    sd = syn.make_dit_state_dict(inp["arch"], seed=case["wseed"])
+    out, traj = orc.cfm_sample(sd, inp["arch"], inp["cond"], inp["text"], inp["duration"], lens=inp["lens"],
+                               steps=case["steps"], cfg_strength=case["cfg"], sway_sampling_coef=case["sway"],
+                               noise=inp["noise"], edit_mask=inp["edit_mask"], use_acc_grl=case["use_acc_grl"])
+    assert out.shape == gold["out"].shape
+    assert (traj[1] - gold["first_step"]).abs().max() < TOL
+    assert (traj[-1] - gold["last"]).abs().max() < TOL * 5
+    assert (out - gold["out"]).abs().max() < TOL * 5
+
+
+@pytest.mark.parametrize("name", ["sample_tiny_b3_ragged", "sample_tiny_edit"])
+def test_backbone_forward_matches_reference(name):
+    case = gc.CASES[name]
+    gold = gc.load(name)
+    inp = gc.inputs(case)
+    arch = inp["arch"]
+    sd = syn.make_dit_state_dict(arch, seed=case["wseed"])
+    N = gold["last"].shape[1]
+    mask = None
+    if case["batch"] > 1:
+        mask = torch.arange(N)[None] < torch.tensor(inp["durations"])[:, None]
+    cond = torch.nn.functional.pad(inp["cond"], (0, 0, 0, N - inp["cond"].shape[1]))
+    t = torch.tensor(0.37)
+    for drop, key in ((False, "fwd_cond"), (True, "fwd_uncond")):
+        te = orc.text_embedding(sd, arch, inp["text"], N, drop_text=drop)
+        got = orc.dit_forward(sd, arch, gold["last"], cond, te, t, mask, drop_audio_cond=drop)
+        assert (got - gold[key]).abs().max() < TOL
+
+
+def test_time_grids_match_reference():
+    grids = torch.load(gc.GOLDEN / "time_grids.pt", weights_only=True)
+    for key, want in grids.items():
+        steps, coef = key.split("_")
+        coef = None if coef == "None" else float(coef)
+        got = orc.time_grid(int(steps), coef)
+        assert torch.equal(got, want), key
+
+
+def test_melspec_matches_reference():
+    want = torch.load(gc.GOLDEN / "melspec.pt", weights_only=True)["mel"]
+    got = orc.mel_spectrogram(syn.synthetic_ref_audio(2, 24000, seed=9))
+    assert (got - want).abs().max() < 1e-5
+
+
+def test_edit_mask_keeps_reference_region_bit_exact():
+    case = gc.CASES["sample_tiny_edit"]
+    inp = gc.inputs(case)
+    gold = gc.load("sample_tiny_edit")
+    keep = torch.ones(150, dtype=torch.bool)
+    keep[case["edit"][0]: case["edit"][1]] = False
+    assert torch.equal(gold["out"][0, :150][keep], inp["cond"][0][keep])
