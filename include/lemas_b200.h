@@ -1,0 +1,218 @@
+/*
+ * lemas_b200.h — C ABI of liblemas_b200.so: the B200 (sm_100a) implementation of the LEMAS-TTS acoustic hot path.
+ *
+ * The reference (LEMAS-Project/LEMAS-TTS) has NO native layer or FFI: its hot path is Python calling stock
+ * PyTorch ops.  Each entry point below therefore replaces a *Python call site* of the reference (cited as
+ * file:line relative to the reference root) rather than an existing native binding.  INTEGRATION.md shows the
+ * ctypes stub a maintainer adds at those call sites; lemas-tts_b200/lemas_tts/_native.py is that stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in _host
+ *  - no hidden allocation: callers pass workspaces (sizes from the *_workspace_bytes functions)
+ *  - every launch goes to the given cudaStream_t (passed as void*); nothing synchronises the device
+ *  - return value 0 = ok, otherwise an error code; lemas_last_error() gives a thread-local message
+ *  - activations that feed tensor cores are fp16, accumulators / residual stream / ODE state are fp32
+ */
+#ifndef LEMAS_B200_H
+#define LEMAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEMAS_OK 0
+#define LEMAS_ERR_INVALID 1
+#define LEMAS_ERR_CUDA 2
+#define LEMAS_ERR_UNSUPPORTED 3
+
+const char* lemas_last_error(void);
+int lemas_version(void);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMA kernels can run), else 0. */
+int lemas_device_supported(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Op-level entry points (one kernel launch each).  Used by the engine below and by the op-level parity tests.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* GEMM epilogues.  acc = A·Wᵀ (fp16 operands, fp32 accumulate in TMEM). */
+enum lemas_epilogue {
+  LEMAS_EPI_BIAS_F16 = 0,       /* out16 = acc + bias                                                          */
+  LEMAS_EPI_QKV_ROPE = 1,       /* modules.py:452-480: +bias; RoPE on q,k heads; q,k -> out16, v -> transposed */
+  LEMAS_EPI_GELU_TANH_F16 = 2,  /* modules.py:348-349: out16 = gelu_tanh(acc + bias)                            */
+  LEMAS_EPI_GELU_ERF_F16 = 3,   /* vocos ConvNeXtBlock: out16 = gelu(acc + bias)                                */
+  LEMAS_EPI_GATE_RESID_F32 = 4, /* modules.py:635,639: out32 = resid + gate[b,col]*mask_rows(acc + bias)        */
+  LEMAS_EPI_BIAS_F32 = 5,       /* out32 = acc + bias                                                           */
+  LEMAS_EPI_ADD_F32_F16 = 6,    /* dit.py:97 split: out32 = acc + addend[row,col]; out16 = same in fp16         */
+  LEMAS_EPI_MISH_F16 = 7,       /* modules.py:172-173: out16 = mish(acc + bias)                                 */
+  LEMAS_EPI_MISH_RESID_F32 = 8  /* modules.py:174-175 + dit.py:98: out32 = mish(acc + bias) + resid             */
+};
+
+typedef struct lemas_gemm_desc {
+  /* A: fp16 activations viewed as [batches, rows, lda] (row-major, lda in elements, multiple of 8).
+   * "taps" > 1 turns the GEMM into an im2col-free 1-D convolution along rows: k-iteration (tap, kc) reads rows
+   * shifted by (tap - tap_pad) with zero fill outside [0, rows) of the same batch item (TMA out-of-bounds fill). */
+  const void* a;
+  int32_t batches, rows, lda;
+  int32_t a_cols;          /* valid A columns (tensor-map inner extent; reads beyond are zero-filled)           */
+  /* W: fp16 [w_rows, ldw] row-major ("out x in", K contiguous — nn.Linear layout). For taps>1 the weight is
+   * tap-major: row (tap*w_tap_stride + out_channel). */
+  const void* w;
+  int32_t w_rows, ldw;
+  int32_t n;               /* output columns                                                                   */
+  int32_t k_per_tap;       /* reduction length per tap, multiple of 64                                         */
+  int32_t taps, tap_pad, w_tap_stride;
+  int32_t group_cols;      /* grouped conv: A column offset = (n0 / block_n) * group_cols (0 = dense)           */
+  int32_t block_n;         /* 64, 128 or 256                                                                    */
+  int32_t epilogue;        /* enum lemas_epilogue                                                               */
+  const float* bias;       /* [n] or NULL                                                                       */
+  void* out16; int32_t ld16;
+  float* out32; int32_t ld32;
+  const float* resid; int32_t ldr;      /* residual / addend, fp32                                             */
+  const float* gate; int32_t gate_bstride; /* per-column gate, + b*gate_bstride                                 */
+  const int32_t* row_valid;  /* [batches_seq] rows >= row_valid[b] contribute zero (modules.py:499-501) or NULL */
+  int32_t seq_len;           /* rows per sequence for (b, pos) = divmod(global_row, seq_len)                    */
+  const float* rope;         /* [seq_len, 32, 2] cos,sin (LEMAS_EPI_QKV_ROPE)                                   */
+  int32_t rope_cols;         /* q/k columns that get RoPE per projection (pe_attn_head*64 or inner)             */
+  int32_t inner;             /* heads*64: columns [0,inner)=q, [inner,2*inner)=k, rest=v                        */
+  void* vt; int32_t vt_ld;   /* V transposed out: fp16 [b, head, 64, vt_ld]                                     */
+  int32_t max_ctas;          /* 0 = one persistent CTA per SM                                                   */
+} lemas_gemm_desc;
+
+int lemas_gemm_f16(const lemas_gemm_desc* d, void* stream);
+
+/* LayerNorm(eps 1e-6, no affine) * (1 + scale) + shift -> fp16   (modules.py:314, :637, :335).
+ * x: fp32 [rows, dim]; scale/shift: fp32 [dim] (+ b*mod_bstride, b = row / seq_len). */
+int lemas_ln_modulate(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
+                      int32_t rows, int32_t dim, int32_t seq_len, void* stream);
+
+/* LayerNorm with affine weight/bias, fp32 in -> fp16 and/or fp32 out (vocos backbone norms). */
+int lemas_ln_affine(const float* x, const float* weight, const float* bias, void* out16, float* out32,
+                    int32_t rows, int32_t dim, float eps, void* stream);
+
+/* Self-attention over [b, seq, heads*64] (modules.py:483-491): softmax(q·kᵀ/8 + keymask)·v.
+ * qk: fp16 [b*seq, ld_qk] with q at column 0 and k at column `inner`; vt: fp16 [b, heads, 64, vt_ld];
+ * kv_len: int32 [b] valid keys per batch item (NULL = seq).  out: fp16 [b*seq, inner]. */
+int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
+                        void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream);
+
+/* y[m, n] = act_in(x)[m, :] · W[n, :] + b[n], all fp32, m <= 64 (time MLP, AdaLN linears: modules.py:311,332,725).
+ * act_in: 0 = identity, 1 = SiLU.  act_out: 0 = identity, 1 = SiLU. */
+int lemas_skinny_linear_f32(const float* x, const float* w, const float* b, float* y, int32_t m, int32_t k,
+                            int32_t n, int32_t act_in, int32_t act_out, void* stream);
+
+/* Sinusoidal time features (modules.py:149-161): out[m, 0:128] = sin(1000 t_m w_k), out[m,128:256] = cos(...). */
+int lemas_time_sinusoid(const float* t, float* out, int32_t m, void* stream);
+
+/* cat(cond | 0, text) -> fp16 A operand of the step-invariant half of the input projection (dit.py:93-97).
+ * rows [0, B*N): (cond, text_c); rows [B*N, 2B*N): (0, text_u).  Output row stride ld (zero padded). */
+int lemas_pack_cond_text(const float* cond, const float* text_c, const float* text_u, void* out16, int32_t rows,
+                         int32_t mel, int32_t text_dim, int32_t ld, int32_t n_variants, void* stream);
+
+/* fp32 [rows, cols] -> fp16 [copies][rows, ld] zero padded. */
+int lemas_cast_pad_f16(const float* x, void* out16, int32_t rows, int32_t cols, int32_t ld, int32_t copies,
+                       void* stream);
+
+/* CFG + clamp + Euler (cfm.py:420-424 and the torchdiffeq Euler step):
+ *   f = cfg>=1e-5 ? clamp(pc + (pc - pu) * cfg * (1-t)^2, -20, 20) : pc ;  y += dt * f
+ * pred: fp32 [2 or 1][rows, ld_pred]; y: fp32 [rows, mel]; also refreshes the fp16 copy of y (x16, `copies` times)
+ * and optionally stores the new state to traj_out. */
+int lemas_cfg_euler(const float* pred, int32_t ld_pred, float* y, void* x16, int32_t ld_x16, int32_t copies,
+                    float* traj_out, int32_t rows, int32_t mel, float t, float dt, float cfg_strength,
+                    void* stream);
+
+/* Depthwise conv k=7 (pad 3) along time + LayerNorm(affine, eps 1e-6) -> fp16   (vocos ConvNeXtBlock).
+ * x: fp32 [b, t, dim]; dw_w: fp32 [7, dim] (tap-major), others fp32 [dim]. */
+int lemas_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
+                     void* out16, int32_t batch, int32_t t, int32_t dim, void* stream);
+
+/* ISTFT head tail (vocos ISTFTHead + torch.istft(center=True), n_fft 1024, hop 256, hann):
+ * head: fp32 [b*t, ld_head] rows = (log-magnitude[513] | phase[513]); wav: fp32 [b, (t-1)*256]; frames: workspace
+ * fp32 [b, t, 1024]. */
+int lemas_istft_1024(const float* head, int32_t ld_head, float* frames_ws, float* wav, int32_t batch, int32_t t,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Engine-level entry points: the whole sampler / vocoder as a sequence of the launches above, driven from C++.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+typedef struct lemas_dit_config {
+  int32_t dim, depth, heads, ff_mult, text_dim, mel_dim, rope_heads;
+} lemas_dit_config;
+
+typedef struct lemas_dit_layer {
+  const void* w_qkv; const float* b_qkv;  /* fp16 [3*inner, dim]; fp32 [3*inner]   (to_q|to_k|to_v stacked)    */
+  const void* w_out; const float* b_out;  /* fp16 [dim, inner]                                                  */
+  const void* w_ff1; const float* b_ff1;  /* fp16 [dim*ff_mult, dim]                                            */
+  const void* w_ff2; const float* b_ff2;  /* fp16 [dim, dim*ff_mult]                                            */
+} lemas_dit_layer;
+
+typedef struct lemas_dit_weights {
+  const float* time_w0; const float* time_b0;   /* fp32 [dim,256],[dim]     transformer.time_embed.time_mlp.0   */
+  const float* time_w2; const float* time_b2;   /* fp32 [dim,dim],[dim]     transformer.time_embed.time_mlp.2   */
+  const float* adaln_w; const float* adaln_b;   /* fp32 [depth*6*dim + 2*dim, dim]: blocks' attn_norm.linear
+                                                   stacked in order, then norm_out.linear                      */
+  const void* w_in_x;                           /* fp16 [dim, 128]   input_embed.proj columns of x (zero pad)   */
+  const void* w_in_ct; const float* b_in;       /* fp16 [dim, ct_ld] columns of (cond | text), zero padded      */
+  int32_t ct_ld;
+  const void* conv_w[2]; const float* conv_b[2];/* fp16 tap-major conv_pos_embed.conv1d.{0,2}: [31*dim, dim/16] when
+                                                   dim/16 == 64 (grouped path), else block-diagonal [31*dim, dim]  */
+  int32_t conv_dense;                           /* 0: grouped path (dim == 1024); 1: block-diagonal dense weights   */
+  const void* w_proj; const float* b_proj;      /* fp16 [128, dim] (rows >= mel_dim zero), fp32 [mel_dim]       */
+  const lemas_dit_layer* layers;                /* host array [depth]                                           */
+} lemas_dit_weights;
+
+typedef struct lemas_engine lemas_engine;
+
+int64_t lemas_engine_workspace_bytes(const lemas_dit_config* cfg, int32_t batch, int32_t seq, int32_t steps);
+int lemas_engine_create(const lemas_dit_config* cfg, const lemas_dit_weights* w, lemas_engine** out);
+void lemas_engine_destroy(lemas_engine* e);
+
+typedef struct lemas_sample_args {
+  int32_t batch, seq, steps;
+  const float* t_grid_host;   /* [steps+1] host floats (cfm.py:445-453)                                        */
+  float cfg_strength;
+  float* y;                   /* in: y0 noise, out: final state; fp32 [batch, seq, mel]                         */
+  const float* step_cond;     /* fp32 [batch, seq, mel]   (cfm.py:387-390, already masked)                      */
+  const float* text_cond;     /* fp32 [batch, seq, text_dim] (dit.py:212-220 cached embeds)                     */
+  const float* text_uncond;
+  const int32_t* kv_len;      /* int32 [batch] = duration per row (mask of cfm.py:336-337), NULL when batch==1  */
+  const float* rope;          /* fp32 [seq, 32, 2] cos/sin table                                                */
+  float* trajectory;          /* optional fp32 [steps+1, batch, seq, mel] (cfm.py:456), NULL to skip            */
+  void* workspace; int64_t workspace_bytes;
+  int32_t use_graph;          /* 1: capture one ODE step into a CUDA graph and replay it                        */
+} lemas_sample_args;
+
+/* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */
+int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream);
+
+/* One DiT.forward (dit.py:194-254) on the co-batched cond/uncond rows; pred: fp32 [2*batch*seq, 128]. Testing aid. */
+int lemas_dit_forward(lemas_engine* e, const lemas_sample_args* a, float t, float* pred, float* hidden_out,
+                      void* stream);
+
+typedef struct lemas_vocos_layer {
+  const float* dw_w; const float* dw_b; const float* ln_w; const float* ln_b;  /* fp32 [dim,7],[dim],[dim],[dim] */
+  const void* w1; const float* b1;     /* fp16 [inter, dim] */
+  const void* w2; const float* b2;     /* fp16 [dim, inter] */
+  const float* gamma;                  /* fp32 [dim]        */
+} lemas_vocos_layer;
+
+typedef struct lemas_vocos_weights {
+  int32_t dim, inter, layers, in_ch;
+  const void* embed_w; const float* embed_b;        /* fp16 [7*dim, 128] tap-major, fp32 [dim]                  */
+  const float* norm_w; const float* norm_b;
+  const lemas_vocos_layer* blocks;                  /* host array [layers]                                      */
+  const float* final_w; const float* final_b;
+  const void* head_w; const float* head_b;          /* fp16 [1152, dim] (rows >= 1026 zero), fp32 [1026]        */
+} lemas_vocos_weights;
+
+int64_t lemas_vocos_workspace_bytes(const lemas_vocos_weights* w, int32_t batch, int32_t t);
+/* Vocos.decode (utils_infer.py:549): mel fp32 [batch, in_ch, t] -> wav fp32 [batch, (t-1)*256]. */
+int lemas_vocos_decode(const lemas_vocos_weights* w, const float* mel, float* wav, int32_t batch, int32_t t,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEMAS_B200_H */

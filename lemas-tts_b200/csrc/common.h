@@ -1,0 +1,43 @@
+// Host-side helpers shared by the translation units of liblemas_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/lemas_b200.h"
+
+namespace lemas {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int sm_count();
+
+#define LEMAS_CUDA_OK(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::lemas::fail(LEMAS_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) +    \
+                                               " at " __FILE__ ":" + std::to_string(__LINE__));      \
+  } while (0)
+
+#define LEMAS_REQUIRE(cond, msg)                                                   \
+  do {                                                                             \
+    if (!(cond)) return ::lemas::fail(LEMAS_ERR_INVALID, std::string(msg));        \
+  } while (0)
+
+#define LEMAS_TRY(expr)            \
+  do {                             \
+    int _rc = (expr);              \
+    if (_rc != LEMAS_OK) return _rc; \
+  } while (0)
+
+// fp16 row-major tensor map with a 64-element (128 B) inner box and the 128-byte swizzle.
+// dims/strides innermost first; strides in bytes for dims 1.. (multiples of 16).
+int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace lemas

@@ -1,0 +1,371 @@
+// Host-side driver of the hot path: CFM.sample's ODE loop (cfm.py:382-456) over the co-batched cond/uncond
+// DiT forward (dit.py:194-254), and Vocos.decode.  Pure launch sequencing — every FLOP is in the kernels of
+// gemm.cu / attention.cu / elementwise.cu.  No allocation: the caller's workspace is carved up here.
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace lemas {
+
+int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream);
+
+struct Carver {
+  uint8_t* base;
+  int64_t off = 0;
+  explicit Carver(void* p) : base(static_cast<uint8_t*>(p)) {}
+  template <class T>
+  T* take(int64_t count) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+struct DitBuffers {
+  __half *x16, *ct16, *h0_16, *c1_16, *a16, *o16, *qk16, *vt16, *ff16;
+  float *inv_embed, *h0, *x, *pred, *t_dev, *sinus, *t1, *temb, *mod;
+  int* kv_len2;
+  int npad;
+  int64_t bytes;
+};
+
+static DitBuffers carve(const lemas_dit_config& c, int batch, int seq, int steps, int ct_ld, void* ws) {
+  DitBuffers b;
+  Carver cv(ws);
+  const int64_t M2 = 2LL * batch * seq;
+  const int D = c.dim, inner = c.heads * 64, F = c.dim * c.ff_mult;
+  b.npad = (int)align_up(seq, 64);
+  b.x16 = cv.take<__half>(M2 * 128);
+  b.ct16 = cv.take<__half>(M2 * ct_ld);
+  b.inv_embed = cv.take<float>(M2 * D);
+  b.h0 = cv.take<float>(M2 * D);
+  b.h0_16 = cv.take<__half>(M2 * D);
+  b.c1_16 = cv.take<__half>(M2 * D);
+  b.x = cv.take<float>(M2 * D);
+  b.a16 = cv.take<__half>(M2 * D);
+  b.o16 = cv.take<__half>(M2 * inner);
+  b.qk16 = cv.take<__half>(M2 * 2 * inner);
+  b.vt16 = cv.take<__half>(2LL * batch * inner * b.npad);
+  b.ff16 = cv.take<__half>(M2 * F);
+  b.pred = cv.take<float>(M2 * 128);
+  b.t_dev = cv.take<float>(steps + 1);
+  b.sinus = cv.take<float>((int64_t)steps * 256);
+  b.t1 = cv.take<float>((int64_t)steps * D);
+  b.temb = cv.take<float>((int64_t)steps * D);
+  b.mod = cv.take<float>((int64_t)steps * ((int64_t)c.depth * 6 * D + 2 * D));
+  b.kv_len2 = cv.take<int>(2 * batch);
+  b.bytes = align_up(cv.off, 1024);
+  return b;
+}
+
+}  // namespace lemas
+
+using namespace lemas;
+
+struct lemas_engine {
+  lemas_dit_config cfg;
+  lemas_dit_weights w;
+  std::vector<lemas_dit_layer> layers;
+};
+
+static int ct_ld_for(const lemas_dit_config* c) { return (int)align_up(c->mel_dim + c->text_dim, 64); }
+
+extern "C" {
+
+int64_t lemas_engine_workspace_bytes(const lemas_dit_config* cfg, int32_t batch, int32_t seq, int32_t steps) {
+  if (!cfg) return -1;
+  return carve(*cfg, batch, seq, steps, ct_ld_for(cfg), nullptr).bytes;
+}
+
+int lemas_engine_create(const lemas_dit_config* cfg, const lemas_dit_weights* w, lemas_engine** out) {
+  LEMAS_REQUIRE(cfg && w && out, "lemas_engine_create: null argument");
+  LEMAS_REQUIRE(cfg->dim % 128 == 0 && cfg->dim <= 1024, "lemas_engine_create: dim must be a multiple of 128, <= 1024");
+  LEMAS_REQUIRE(cfg->heads >= 1 && cfg->mel_dim <= 128 && cfg->mel_dim >= 1, "lemas_engine_create: bad heads/mel_dim");
+  LEMAS_REQUIRE((cfg->heads * 64) % 64 == 0 && cfg->text_dim >= 1, "lemas_engine_create: bad text_dim");
+  LEMAS_REQUIRE(w->ct_ld == ct_ld_for(cfg), "lemas_engine_create: ct_ld must be round_up(mel_dim + text_dim, 64)");
+  LEMAS_REQUIRE(w->conv_dense == 1 || cfg->dim / 16 == 64, "lemas_engine_create: grouped conv path needs dim == 1024");
+  LEMAS_REQUIRE(w->layers != nullptr, "lemas_engine_create: layers missing");
+  if (!lemas_device_supported())
+    return fail(LEMAS_ERR_UNSUPPORTED,
+                "CUDA error: no kernel image is available for execution on the device (liblemas_b200 is sm_100a only)");
+  auto* e = new lemas_engine;
+  e->cfg = *cfg;
+  e->w = *w;
+  e->layers.assign(w->layers, w->layers + cfg->depth);
+  e->w.layers = e->layers.data();
+  *out = e;
+  return LEMAS_OK;
+}
+
+void lemas_engine_destroy(lemas_engine* e) { delete e; }
+}
+
+namespace lemas {
+
+static lemas_gemm_desc base_desc(const void* a, int batches, int rows, int lda, const void* w, int w_rows, int ldw,
+                                 int n, int seq_len, int epilogue, int block_n) {
+  lemas_gemm_desc d = {};
+  d.a = a; d.batches = batches; d.rows = rows; d.lda = lda; d.a_cols = lda;
+  d.w = w; d.w_rows = w_rows; d.ldw = ldw; d.n = n;
+  d.k_per_tap = ldw; d.taps = 1; d.tap_pad = 0; d.w_tap_stride = 0; d.group_cols = 0;
+  d.block_n = block_n; d.epilogue = epilogue; d.seq_len = seq_len;
+  return d;
+}
+
+// One DiT forward on `variants*batch` co-batched sequences; mod = this step's modulation row.
+static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, int seq, int variants, const float* mod,
+                       const int* kv_len2, const float* rope, float* pred, cudaStream_t st) {
+  const lemas_dit_config& c = e->cfg;
+  const lemas_dit_weights& w = e->w;
+  const int D = c.dim, inner = c.heads * 64, F = c.dim * c.ff_mult;
+  const int B2 = variants * batch;
+  const int M = B2 * seq;
+  const int bn_d = D % 256 == 0 ? 256 : 128;
+
+  {  // dit.py:97  x-columns of the input projection + the precomputed (cond|text) part
+    lemas_gemm_desc d = base_desc(b.x16, 1, M, 128, w.w_in_x, D, 128, D, seq, LEMAS_EPI_ADD_F32_F16, bn_d);
+    d.resid = b.inv_embed; d.ldr = D; d.out32 = b.h0; d.ld32 = D; d.out16 = b.h0_16; d.ld16 = D;
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  for (int j = 0; j < 2; ++j) {  // modules.py:171-176 grouped conv k=31 + Mish, twice; dit.py:98 residual
+    const __half* in = j == 0 ? b.h0_16 : b.c1_16;
+    lemas_gemm_desc d = {};
+    d.a = in; d.batches = B2; d.rows = seq; d.lda = D; d.a_cols = D;
+    d.w = w.conv_w[j]; d.w_rows = 31 * D; d.n = D; d.taps = 31; d.tap_pad = 15; d.w_tap_stride = D;
+    if (w.conv_dense) { d.ldw = D; d.k_per_tap = D; d.group_cols = 0; d.block_n = bn_d; }
+    else { d.ldw = 64; d.k_per_tap = 64; d.group_cols = 64; d.block_n = 64; }
+    d.bias = w.conv_b[j]; d.seq_len = seq;
+    if (j == 0) { d.epilogue = LEMAS_EPI_MISH_F16; d.out16 = b.c1_16; d.ld16 = D; }
+    else { d.epilogue = LEMAS_EPI_MISH_RESID_F32; d.resid = b.h0; d.ldr = D; d.out32 = b.x; d.ld32 = D; }
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  for (int l = 0; l < c.depth; ++l) {
+    const lemas_dit_layer& L = w.layers[l];
+    const float* m = mod + (int64_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
+    LEMAS_TRY(lemas_ln_modulate(b.x, m + D, m, 0, b.a16, M, D, seq, st));
+    {
+      lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_qkv, 3 * inner, D, 3 * inner, seq, LEMAS_EPI_QKV_ROPE, 256);
+      d.bias = L.b_qkv; d.out16 = b.qk16; d.ld16 = 2 * inner; d.rope = rope;
+      d.rope_cols = c.rope_heads * 64; d.inner = inner; d.vt = b.vt16; d.vt_ld = b.npad;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+    LEMAS_TRY(lemas_attention_f16(b.qk16, 2 * inner, b.vt16, b.npad, kv_len2, b.o16, B2, seq, c.heads, st));
+    {
+      lemas_gemm_desc d = base_desc(b.o16, 1, M, inner, L.w_out, D, inner, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
+      d.bias = L.b_out; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 2 * D; d.gate_bstride = 0;
+      d.row_valid = kv_len2;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+    LEMAS_TRY(lemas_ln_modulate(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, st));
+    {
+      lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_ff1, F, D, F, seq, LEMAS_EPI_GELU_TANH_F16, 256);
+      d.bias = L.b_ff1; d.out16 = b.ff16; d.ld16 = F;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+    {
+      lemas_gemm_desc d = base_desc(b.ff16, 1, M, F, L.w_ff2, D, F, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
+      d.bias = L.b_ff2; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 5 * D; d.gate_bstride = 0;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+  }
+  const float* mf = mod + (int64_t)c.depth * 6 * D;  // modules.py:333: (scale, shift)
+  LEMAS_TRY(lemas_ln_modulate(b.x, mf, mf + D, 0, b.a16, M, D, seq, st));
+  {
+    lemas_gemm_desc d = base_desc(b.a16, 1, M, D, w.w_proj, 128, D, c.mel_dim, seq, LEMAS_EPI_BIAS_F32, 128);
+    d.bias = w.b_proj; d.out32 = pred; d.ld32 = 128;
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  return LEMAS_OK;
+}
+
+// Everything that does not depend on the ODE state: time embeddings + all AdaLN modulations for every step
+// (modules.py:311,332,725 hoisted), the (cond|text) half of the input projection, fp16 copy of y0.
+static int prepare(const lemas_engine* e, const DitBuffers& b, const lemas_sample_args* a, int variants, int n_times,
+                   const float* times_host, cudaStream_t st) {
+  const lemas_dit_config& c = e->cfg;
+  const lemas_dit_weights& w = e->w;
+  const int D = c.dim;
+  const int rows = a->batch * a->seq;
+  const int64_t mod_w = (int64_t)c.depth * 6 * D + 2 * D;
+  LEMAS_CUDA_OK(cudaMemcpyAsync(b.t_dev, times_host, sizeof(float) * n_times, cudaMemcpyHostToDevice, st));
+  LEMAS_TRY(lemas_time_sinusoid(b.t_dev, b.sinus, n_times, st));
+  LEMAS_TRY(lemas_skinny_linear_f32(b.sinus, w.time_w0, w.time_b0, b.t1, n_times, 256, D, 0, 1, st));
+  LEMAS_TRY(lemas_skinny_linear_f32(b.t1, w.time_w2, w.time_b2, b.temb, n_times, D, D, 0, 0, st));
+  LEMAS_TRY(lemas_skinny_linear_f32(b.temb, w.adaln_w, w.adaln_b, b.mod, n_times, D, (int)mod_w, 1, 0, st));
+  LEMAS_TRY(lemas_cast_pad_f16(a->y, b.x16, rows, c.mel_dim, 128, variants, st));
+  LEMAS_TRY(lemas_pack_cond_text(a->step_cond, a->text_cond, a->text_uncond, b.ct16, rows, c.mel_dim, c.text_dim,
+                                 w.ct_ld, variants, st));
+  {
+    const int bn_d = D % 256 == 0 ? 256 : 128;
+    lemas_gemm_desc d = base_desc(b.ct16, 1, variants * rows, w.ct_ld, w.w_in_ct, D, w.ct_ld, D, a->seq,
+                                  LEMAS_EPI_BIAS_F32, bn_d);
+    d.bias = w.b_in; d.out32 = b.inv_embed; d.ld32 = D;
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  if (a->kv_len) {
+    for (int v = 0; v < variants; ++v)
+      LEMAS_CUDA_OK(cudaMemcpyAsync(b.kv_len2 + v * a->batch, a->kv_len, sizeof(int) * a->batch,
+                                    cudaMemcpyDeviceToDevice, st));
+  }
+  return LEMAS_OK;
+}
+
+static int check_args(const lemas_engine* e, const lemas_sample_args* a, int steps_for_ws, DitBuffers* out) {
+  LEMAS_REQUIRE(e && a, "lemas sampler: null argument");
+  LEMAS_REQUIRE(a->batch >= 1 && a->seq >= 1 && a->seq <= 4096, "lemas sampler: need 1 <= seq <= 4096, batch >= 1");
+  LEMAS_REQUIRE(a->y && a->step_cond && a->text_cond && a->rope && a->workspace, "lemas sampler: null tensor");
+  *out = carve(e->cfg, a->batch, a->seq, steps_for_ws, e->w.ct_ld, a->workspace);
+  LEMAS_REQUIRE(a->workspace_bytes >= out->bytes, "lemas sampler: workspace too small");
+  LEMAS_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 1023) == 0, "lemas sampler: workspace must be 1 KiB aligned");
+  return LEMAS_OK;
+}
+
+}  // namespace lemas
+
+extern "C" {
+
+int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DitBuffers b;
+  LEMAS_TRY(check_args(e, a, a ? a->steps : 0, &b));
+  LEMAS_REQUIRE(a->steps >= 1 && a->t_grid_host, "lemas_sampler_run: steps >= 1 and a t grid are required");
+  const int variants = a->cfg_strength >= 1e-5f ? 2 : 1;
+  LEMAS_REQUIRE(variants == 1 || a->text_uncond, "lemas_sampler_run: text_uncond required when cfg_strength > 0");
+  const lemas_dit_config& c = e->cfg;
+  const int rows = a->batch * a->seq;
+  const int64_t mod_w = (int64_t)c.depth * 6 * c.dim + 2 * c.dim;
+  LEMAS_TRY(prepare(e, b, a, variants, a->steps, a->t_grid_host, st));
+  const int64_t state = (int64_t)rows * c.mel_dim;
+  if (a->trajectory)
+    LEMAS_CUDA_OK(cudaMemcpyAsync(a->trajectory, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
+  const int* kv2 = a->kv_len ? b.kv_len2 : nullptr;
+  for (int i = 0; i < a->steps; ++i) {
+    LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod + i * mod_w, kv2, a->rope, b.pred, st));
+    const float t = a->t_grid_host[i];
+    const float dt = a->t_grid_host[i + 1] - t;
+    float* traj = a->trajectory ? a->trajectory + (int64_t)(i + 1) * state : nullptr;
+    LEMAS_TRY(lemas_cfg_euler(b.pred, 128, a->y, b.x16, 128, variants, traj, rows, c.mel_dim, t, dt,
+                              variants == 2 ? a->cfg_strength : 0.f, st));
+  }
+  return LEMAS_OK;
+}
+
+int lemas_dit_forward(lemas_engine* e, const lemas_sample_args* a, float t, float* pred, float* hidden_out,
+                      void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DitBuffers b;
+  LEMAS_TRY(check_args(e, a, 1, &b));
+  LEMAS_REQUIRE(pred && a->text_uncond, "lemas_dit_forward: pred and text_uncond are required");
+  LEMAS_TRY(prepare(e, b, a, 2, 1, &t, st));
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, 2, b.mod, a->kv_len ? b.kv_len2 : nullptr, a->rope, pred, st));
+  if (hidden_out)
+    LEMAS_CUDA_OK(cudaMemcpyAsync(hidden_out, b.x, sizeof(float) * 2LL * a->batch * a->seq * e->cfg.dim,
+                                  cudaMemcpyDeviceToDevice, st));
+  return LEMAS_OK;
+}
+}
+
+// ------------------------------------------------------------------------------------------------ Vocos
+namespace lemas {
+
+__global__ void mel_to_rows_kernel(const float* __restrict__ mel, __half* __restrict__ out, int batch, int ch, int t) {
+  // [b, ch, t] fp32 -> [b, t, 128] fp16 (zero padded channels)
+  const long total = (long)batch * t * 128;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cidx = (int)(i & 127);
+    const long bt = i >> 7;
+    const int b = (int)(bt / t), tt = (int)(bt - (long)b * t);
+    out[i] = __float2half_rn(cidx < ch ? mel[((long)b * ch + cidx) * t + tt] : 0.f);
+  }
+}
+
+struct VocosBuffers {
+  __half *mel16, *a16, *h16;
+  float *e32, *x32, *head32, *frames;
+  int head_ld;
+  int64_t bytes;
+};
+
+static VocosBuffers carve_vocos(const lemas_vocos_weights& w, int batch, int t, void* ws) {
+  VocosBuffers b;
+  Carver cv(ws);
+  const int64_t R = (int64_t)batch * t;
+  b.head_ld = 1152;
+  b.mel16 = cv.take<__half>(R * 128);
+  b.e32 = cv.take<float>(R * w.dim);
+  b.x32 = cv.take<float>(R * w.dim);
+  b.a16 = cv.take<__half>(R * w.dim);
+  b.h16 = cv.take<__half>(R * w.inter);
+  b.head32 = cv.take<float>(R * b.head_ld);
+  b.frames = cv.take<float>(R * 1024);
+  b.bytes = align_up(cv.off, 1024);
+  return b;
+}
+
+}  // namespace lemas
+
+extern "C" {
+
+int64_t lemas_vocos_workspace_bytes(const lemas_vocos_weights* w, int32_t batch, int32_t t) {
+  if (!w) return -1;
+  return carve_vocos(*w, batch, t, nullptr).bytes;
+}
+
+int lemas_vocos_decode(const lemas_vocos_weights* w, const float* mel, float* wav, int32_t batch, int32_t t,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LEMAS_REQUIRE(w && mel && wav && workspace, "lemas_vocos_decode: null argument");
+  LEMAS_REQUIRE(w->in_ch <= 128 && w->dim % 128 == 0 && w->dim <= 1024 && w->inter % 64 == 0,
+                "lemas_vocos_decode: unsupported dims");
+  LEMAS_REQUIRE(t >= 2 && batch >= 1, "lemas_vocos_decode: need at least 2 frames");
+  if (!lemas_device_supported())
+    return fail(LEMAS_ERR_UNSUPPORTED,
+                "CUDA error: no kernel image is available for execution on the device (liblemas_b200 is sm_100a only)");
+  VocosBuffers b = carve_vocos(*w, batch, t, workspace);
+  LEMAS_REQUIRE(workspace_bytes >= b.bytes, "lemas_vocos_decode: workspace too small");
+  const int R = batch * t;
+  const int dim = w->dim, inter = w->inter;
+  const int bn_dim = dim % 256 == 0 ? 256 : 128;
+  const int bn_inter = inter % 256 == 0 ? 256 : 128;
+  {
+    const long total = (long)R * 128;
+    int grid = (int)((total + 255) / 256);
+    if (grid > sm_count() * 16) grid = sm_count() * 16;
+    mel_to_rows_kernel<<<grid, 256, 0, st>>>(mel, b.mel16, batch, w->in_ch, t);
+    LEMAS_CUDA_OK(cudaGetLastError());
+  }
+  {  // backbone.embed: Conv1d(in_ch -> dim, k=7, pad=3) as a 7-tap GEMM
+    lemas_gemm_desc d = {};
+    d.a = b.mel16; d.batches = batch; d.rows = t; d.lda = 128; d.a_cols = 128;
+    d.w = w->embed_w; d.w_rows = 7 * dim; d.ldw = 128; d.n = dim; d.k_per_tap = 128; d.taps = 7; d.tap_pad = 3;
+    d.w_tap_stride = dim; d.block_n = bn_dim; d.epilogue = LEMAS_EPI_BIAS_F32; d.bias = w->embed_b;
+    d.out32 = b.e32; d.ld32 = dim; d.seq_len = t;
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  LEMAS_TRY(lemas_ln_affine(b.e32, w->norm_w, w->norm_b, nullptr, b.x32, R, dim, 1e-6f, st));
+  for (int l = 0; l < w->layers; ++l) {
+    const lemas_vocos_layer& L = w->blocks[l];
+    LEMAS_TRY(lemas_dwconv7_ln(b.x32, L.dw_w, L.dw_b, L.ln_w, L.ln_b, b.a16, batch, t, dim, st));
+    {
+      lemas_gemm_desc d = base_desc(b.a16, 1, R, dim, L.w1, inter, dim, inter, t, LEMAS_EPI_GELU_ERF_F16, bn_inter);
+      d.bias = L.b1; d.out16 = b.h16; d.ld16 = inter;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+    {
+      lemas_gemm_desc d = base_desc(b.h16, 1, R, inter, L.w2, dim, inter, dim, t, LEMAS_EPI_GATE_RESID_F32, bn_dim);
+      d.bias = L.b2; d.resid = b.x32; d.ldr = dim; d.out32 = b.x32; d.ld32 = dim; d.gate = L.gamma; d.gate_bstride = 0;
+      LEMAS_TRY(gemm_launch(d, st));
+    }
+  }
+  LEMAS_TRY(lemas_ln_affine(b.x32, w->final_w, w->final_b, b.a16, nullptr, R, dim, 1e-6f, st));
+  {
+    lemas_gemm_desc d = base_desc(b.a16, 1, R, dim, w->head_w, 1152, dim, 1026, t, LEMAS_EPI_BIAS_F32, 128);
+    d.bias = w->head_b; d.out32 = b.head32; d.ld32 = b.head_ld;
+    LEMAS_TRY(gemm_launch(d, st));
+  }
+  LEMAS_TRY(lemas_istft_1024(b.head32, b.head_ld, b.frames, wav, batch, t, st));
+  return LEMAS_OK;
+}
+}

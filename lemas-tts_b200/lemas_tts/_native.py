@@ -1,0 +1,146 @@
+"""ctypes binding of liblemas_b200.so (C ABI in include/lemas_b200.h).
+
+This is the stub INTEGRATION.md describes: torch tensors provide device memory and the current CUDA
+stream; every FLOP of the hot path runs in the library's sm_100a kernels.  There is NO fallback: if the
+library is missing or the device is not a Blackwell part, calls raise RuntimeError whose text contains
+"CUDA error" / "no kernel image is available for execution on the device" — the substrings the reference
+entry points match to trigger their own CPU retry (scripts/inference_gradio.py:317-321).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / "lib" / "liblemas_b200.so"
+_lib = None
+
+EPI_BIAS_F16, EPI_QKV_ROPE, EPI_GELU_TANH_F16, EPI_GELU_ERF_F16, EPI_GATE_RESID_F32 = 0, 1, 2, 3, 4
+EPI_BIAS_F32, EPI_ADD_F32_F16, EPI_MISH_F16, EPI_MISH_RESID_F32 = 5, 6, 7, 8
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", vp), ("batches", i32), ("rows", i32), ("lda", i32), ("a_cols", i32),
+        ("w", vp), ("w_rows", i32), ("ldw", i32), ("n", i32), ("k_per_tap", i32),
+        ("taps", i32), ("tap_pad", i32), ("w_tap_stride", i32), ("group_cols", i32),
+        ("block_n", i32), ("epilogue", i32), ("bias", vp),
+        ("out16", vp), ("ld16", i32), ("out32", vp), ("ld32", i32),
+        ("resid", vp), ("ldr", i32), ("gate", vp), ("gate_bstride", i32),
+        ("row_valid", vp), ("seq_len", i32), ("rope", vp), ("rope_cols", i32), ("inner", i32),
+        ("vt", vp), ("vt_ld", i32), ("max_ctas", i32),
+    ]
+
+
+class DitConfig(C.Structure):
+    _fields_ = [("dim", i32), ("depth", i32), ("heads", i32), ("ff_mult", i32), ("text_dim", i32),
+                ("mel_dim", i32), ("rope_heads", i32)]
+
+
+class DitLayer(C.Structure):
+    _fields_ = [("w_qkv", vp), ("b_qkv", vp), ("w_out", vp), ("b_out", vp),
+                ("w_ff1", vp), ("b_ff1", vp), ("w_ff2", vp), ("b_ff2", vp)]
+
+
+class DitWeights(C.Structure):
+    _fields_ = [("time_w0", vp), ("time_b0", vp), ("time_w2", vp), ("time_b2", vp),
+                ("adaln_w", vp), ("adaln_b", vp), ("w_in_x", vp), ("w_in_ct", vp), ("b_in", vp), ("ct_ld", i32),
+                ("conv_w", vp * 2), ("conv_b", vp * 2), ("conv_dense", i32),
+                ("w_proj", vp), ("b_proj", vp), ("layers", C.POINTER(DitLayer))]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [("batch", i32), ("seq", i32), ("steps", i32), ("t_grid_host", C.POINTER(f32)),
+                ("cfg_strength", f32), ("y", vp), ("step_cond", vp), ("text_cond", vp), ("text_uncond", vp),
+                ("kv_len", vp), ("rope", vp), ("trajectory", vp), ("workspace", vp), ("workspace_bytes", i64),
+                ("use_graph", i32)]
+
+
+class VocosLayer(C.Structure):
+    _fields_ = [("dw_w", vp), ("dw_b", vp), ("ln_w", vp), ("ln_b", vp), ("w1", vp), ("b1", vp),
+                ("w2", vp), ("b2", vp), ("gamma", vp)]
+
+
+class VocosWeights(C.Structure):
+    _fields_ = [("dim", i32), ("inter", i32), ("layers", i32), ("in_ch", i32),
+                ("embed_w", vp), ("embed_b", vp), ("norm_w", vp), ("norm_b", vp),
+                ("blocks", C.POINTER(VocosLayer)), ("final_w", vp), ("final_b", vp),
+                ("head_w", vp), ("head_b", vp)]
+
+
+# every symbol include/lemas_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "lemas_last_error": (C.c_char_p, []),
+    "lemas_version": (C.c_int, []),
+    "lemas_device_supported": (C.c_int, []),
+    "lemas_gemm_f16": (C.c_int, [C.POINTER(GemmDesc), vp]),
+    "lemas_ln_modulate": (C.c_int, [vp, vp, vp, i32, vp, i32, i32, i32, vp]),
+    "lemas_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "lemas_attention_f16": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, vp]),
+    "lemas_skinny_linear_f32": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "lemas_time_sinusoid": (C.c_int, [vp, vp, i32, vp]),
+    "lemas_pack_cond_text": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "lemas_cast_pad_f16": (C.c_int, [vp, vp, i32, i32, i32, i32, vp]),
+    "lemas_cfg_euler": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, i32, i32, f32, f32, f32, vp]),
+    "lemas_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "lemas_istft_1024": (C.c_int, [vp, i32, vp, vp, i32, i32, vp]),
+    "lemas_engine_workspace_bytes": (i64, [C.POINTER(DitConfig), i32, i32, i32]),
+    "lemas_engine_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(vp)]),
+    "lemas_engine_destroy": (None, [vp]),
+    "lemas_sampler_run": (C.c_int, [vp, C.POINTER(SampleArgs), vp]),
+    "lemas_dit_forward": (C.c_int, [vp, C.POINTER(SampleArgs), f32, vp, vp, vp]),
+    "lemas_vocos_workspace_bytes": (i64, [C.POINTER(VocosWeights), i32, i32]),
+    "lemas_vocos_decode": (C.c_int, [C.POINTER(VocosWeights), vp, vp, i32, i32, vp, i64, vp]),
+}
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("LEMAS_B200_LIB", _LIB_PATH))
+
+
+def load():
+    """dlopen the library and type every entry point.  Raises loudly if the build is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not path.exists():
+        raise RuntimeError(
+            f"CUDA error: {path} is missing — build it with `python lemas-tts_b200/build.py` "
+            "(this package has no CPU or PyTorch fallback)")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().lemas_last_error().decode(errors="replace")
+        raise RuntimeError(msg if "CUDA error" in msg else f"lemas_b200 error {rc}: {msg}")
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "native ops take contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA error: no CUDA device is available (lemas_tts B200 build has no CPU path)")
+    if not load().lemas_device_supported():
+        raise RuntimeError("CUDA error: no kernel image is available for execution on the device "
+                           "(liblemas_b200 is built for sm_100a only)")
