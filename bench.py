@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — mel-frames/s and RTF of the LEMAS-TTS acoustic hot path (CFM.sample + Vocos.decode) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|C4|C5|C1] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one full synthesis of the workload's utterance batch on each GPU: the 32-NFE ODE loop (64 co-batched DiT
+forwards) and the vocoder.  Workload at N=1 = BASELINE.json configs[1] ("C2": batch 1, 10 s reference = 937 mel
+frames, 350 phones, 1250 generated frames, NFE 32, CFG 2.0, sway 5 -> 3.4856).  N>1 = one such replica per GPU
+(utterance sharding, no data-path collective, weak scaling); weights are broadcast once from rank 0 over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = generated mel frames / s with inputs resident in HBM; `e2e` = the same
+through the public API (CFM.sample + vocoder.decode) from pinned HOST buffers, H2D and D2H copies inside the timed
+region; `roofline` = the attention kernel (the largest tensor-core kernel of the step) from CUDA events recorded
+around each of its launches in a profiled step of the same workload; `cpu_baseline` = the CPU oracle port timed on
+this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "lemas-tts_b200"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+import torch  # noqa: E402
+
+from lemas_tts import synthetic as syn  # noqa: E402
+
+METRIC, UNIT = "mel_frames_per_sec", "mel-frames/s"
+HOP, SR = 256, 24000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=list(syn.CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU utterance batch (C4: default 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def workload(name: str, batch_override: int, n_gpus: int):
+    cfg = syn.CONFIGS[name]
+    batch = cfg.batch
+    if name == "C4":
+        batch = 32  # 256 utterances over 8 GPUs (BASELINE.json configs[3]); per-GPU shard is what one rank runs
+    if batch_override:
+        batch = batch_override
+    return cfg, batch
+
+
+def make_inputs(cfg, batch: int, seed: int):
+    arch = syn.FULL_ARCH
+    cond = syn.synthetic_ref_mel(batch, cfg.ref_frames, arch.mel_dim, seed=seed)
+    text = syn.synthetic_text_ids(batch, cfg.n_text, arch.text_num_embeds, seed=seed)
+    edit_mask = None
+    if cfg.name == "C5":  # speech edit: regenerate 3 s in the middle, keep the rest
+        edit_mask = torch.ones(batch, cfg.ref_frames, dtype=torch.bool)
+        edit_mask[:, 1125:1406] = False
+    return cond, text, edit_mask
+
+
+def generated_frames(cfg, batch: int) -> int:
+    if cfg.name == "C5":
+        return batch * cfg.total_frames  # the whole utterance is re-vocoded (speech_edit_multilingual.py:198)
+    return batch * (cfg.total_frames - cfg.ref_frames)
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(tflops=d["bf16_tflops_sustained"], tflops_burst=d["bf16_tflops"], hbm=d["hbm_gbs"],
+                    source="MEASURED_PEAKS.json (sustained bf16 GEMM; kernel timed inside a long step)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arm
+
+
+def cpu_oracle_sample(cfg, batch: int, euler_steps: int = 1):
+    """Times the CPU oracle (oracle/lemas_oracle.py + vocos_oracle.py, fp32, all host threads) on a bounded sample of
+    the workload: text embedding (2 passes), `euler_steps` Euler steps (2 DiT forwards each) at the full sequence
+    length, and the vocoder on the generated frames.  The ODE loop is linear in steps, so it is scaled to cfg.steps."""
+    from oracle import lemas_oracle as orc
+    from oracle import vocos_oracle as vo
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    arch = syn.FULL_ARCH
+    sd = syn.make_dit_state_dict(arch, seed=0)
+    vsd = syn.make_vocos_state_dict(syn.FULL_VOCOS, seed=7)
+    cond, text, _ = make_inputs(cfg, batch, seed=cfg.seed)
+    N = cfg.total_frames
+    noise = syn.synthetic_noise([N] * batch, arch.mel_dim, seed=cfg.seed)
+    condp = torch.nn.functional.pad(cond, (0, 0, 0, N - cond.shape[1]))
+    mask = orc.lens_to_mask(torch.full((batch,), N)) if batch > 1 else None
+    tgrid = orc.time_grid(cfg.steps, cfg.sway_coef)
+    with torch.inference_mode():
+        t0 = time.perf_counter()
+        tc = orc.text_embedding(sd, arch, text, N, drop_text=False)
+        tu = orc.text_embedding(sd, arch, text, N, drop_text=True)
+        t_text = time.perf_counter() - t0
+        y = noise
+        t0 = time.perf_counter()
+        for i in range(euler_steps):
+            t = tgrid[i]
+            pc = orc.dit_forward(sd, arch, y, condp, tc, t, mask, False)
+            pu = orc.dit_forward(sd, arch, y, condp, tu, t, mask, True)
+            y = y + (tgrid[i + 1] - t) * (pc + (pc - pu) * (cfg.cfg_strength * (1 - t) ** 2)).clamp(-20, 20)
+        t_step = (time.perf_counter() - t0) / euler_steps
+        gen = generated_frames(cfg, batch) // batch
+        mel = y[:, -gen:].transpose(1, 2).contiguous()
+        t0 = time.perf_counter()
+        vo.vocos_decode(vsd, mel)
+        t_voc = time.perf_counter() - t0
+    total = t_text + cfg.steps * t_step + t_voc
+    return dict(seconds=total, t_text=t_text, t_step=t_step, t_vocos=t_voc, cores=cores,
+                sample=f"oracle port, fp32, {cores} threads: text-embed x2 + {euler_steps} Euler step(s) "
+                       f"(2 DiT forwards each, B={batch}, N={N}) scaled to {cfg.steps} steps + Vocos decode of {gen} frames")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port — the reference needs
+    un-vendored packages that are absent offline, so it cannot be installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, batch = workload(args.workload, args.batch, args.gpus)
+    frames = generated_frames(cfg, batch)
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_oracle_sample(cfg, batch, euler_steps=1)
+        if i >= args.warmup:
+            times.append(info["seconds"])
+    sec = sum(times) / len(times)
+    value = frames / sec
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "rtf": sec / (frames * HOP / SR),
+            "config": {"workload": f"{cfg.name}: batch {batch}, ref {cfg.ref_frames} frames, N {cfg.total_frames}, "
+                                   f"NFE {cfg.steps}, cfg {cfg.cfg_strength}, sway {cfg.sway_coef}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                             "sample": info["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    from lemas_tts import _native as nv
+    from lemas_tts.model.backbones.dit import DiT
+    from lemas_tts.model.cfm import CFM
+    from lemas_tts.parallel import broadcast_state_dict, max_over_ranks
+    from lemas_tts.vocoder import Vocos
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    nv.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, batch = workload(args.workload, args.batch, world)
+    arch = syn.FULL_ARCH
+    # weights: rank 0 "loads" (seeded factory), one NCCL broadcast of the packed blob, every rank keeps a replica
+    if world > 1:
+        sd_all = None
+        if rank == 0:
+            sd_all = {**syn.make_dit_state_dict(arch, seed=0),
+                      **{"vocos." + k: v for k, v in syn.make_vocos_state_dict(syn.FULL_VOCOS, seed=7).items()}}
+        sd_all = broadcast_state_dict(sd_all, src=0, device=dev)
+        sd = {k: v for k, v in sd_all.items() if not k.startswith("vocos.")}
+        vsd = {k[6:]: v for k, v in sd_all.items() if k.startswith("vocos.")}
+    else:
+        sd = syn.make_dit_state_dict(arch, seed=0)
+        vsd = syn.make_vocos_state_dict(syn.FULL_VOCOS, seed=7)
+    model = CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    voc = Vocos()
+    voc.load_state_dict(vsd, strict=True)
+    voc = voc.to(dev).eval()
+    del sd, vsd
+
+    cond_h, text_h, edit_h = make_inputs(cfg, batch, seed=cfg.seed + 100 * rank)
+    cond_h, text_h = cond_h.pin_memory(), text_h.pin_memory()
+    cond_d, text_d = cond_h.to(dev), text_h.to(dev)
+    edit_d = None if edit_h is None else edit_h.to(dev)
+    frames = generated_frames(cfg, batch)
+    gen_from = 0 if cfg.name == "C5" else cfg.ref_frames
+    wav_h = torch.empty(batch, (frames // batch - 1) * HOP).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def synth(cond, text, seed):
+        out, _ = model.sample(cond=cond, text=text, duration=cfg.total_frames, steps=cfg.steps,
+                              cfg_strength=cfg.cfg_strength, sway_sampling_coef=cfg.sway_coef, seed=seed,
+                              edit_mask=edit_d, use_acc_grl=False, return_trajectory=False)
+        return voc.decode(out[:, gen_from:, :].permute(0, 2, 1))
+
+    def step_resident(i):
+        return synth(cond_d, text_d, 1000 + i)
+
+    def step_e2e(i):
+        wav = synth(cond_h.to(dev, non_blocking=True), text_h.to(dev, non_blocking=True), 1000 + i)
+        wav_h.copy_(wav, non_blocking=True)
+        return wav
+
+    def timed(fn, n_warm, n_steps):
+        for i in range(n_warm):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        l0 = nv.load().lemas_launch_count()
+        for i in range(n_steps):
+            flush.zero_()  # L2 flush between timed iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(n_warm + i)
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        launches = nv.load().lemas_launch_count() - l0
+        if world > 1:
+            dist.barrier()
+            total = max_over_ranks(total, device=dev)
+        return total, launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_resident, args.warmup, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _ = timed(step_e2e, 1, args.steps)
+
+    # profiled step: CUDA events around every launch of the sampler, by kernel kind (same workload, same process)
+    eng = model.transformer.engine()
+    eng.profile(True)
+    eng.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flush.zero_()
+    e0.record()
+    step_resident(10_000)
+    e1.record()
+    prof = eng.profile_read()
+    eng.profile(False)
+    prof_ms = e0.elapsed_time(e1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    N, D, L = cfg.total_frames, arch.dim, arch.depth
+    variants = 2 if cfg.cfg_strength >= 1e-5 else 1
+    att_ms, att_n = prof["attention"]
+    att_flops = 4.0 * N * N * (arch.heads * 64) * batch * variants  # QK^T + PV, per launch (one layer)
+    att_tflops = att_flops / (att_ms / att_n * 1e-3) / 1e12 if att_n else 0.0
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get(f"attention_{cfg.name}_b{batch}")
+    flops_fwd = N * (378_888_192 + 90_112 * N)
+    dit_flops = variants * cfg.steps * batch * flops_fwd
+    sec_step = ms_total / args.steps * 1e-3
+    kinds = {}
+    for k, (ms, n) in prof.items():
+        if n:
+            kinds[k] = {"ms": round(ms, 3), "launches": n, "share": round(ms / prof_ms, 4)}
+    gemm_flops = {"gemm_qkv": 2.0 * 3 * D * D, "gemm_out": 2.0 * D * D, "gemm_ff1": 2.0 * D * D * arch.ff_mult,
+                  "gemm_ff2": 2.0 * D * D * arch.ff_mult}
+    for k, per_tok in gemm_flops.items():
+        ms, n = prof[k]
+        if n:
+            kinds[k]["tflops"] = round(per_tok * N * batch * variants / (ms / n * 1e-3) / 1e12, 1)
+    if att_n:
+        kinds["attention"]["tflops"] = round(att_tflops, 1)
+    ms, n = prof["ln_mod"]
+    if n:  # algorithmic bytes: read fp32 x, write fp16 (6 B / element)
+        kinds["ln_mod"]["gbs"] = round(6.0 * D * N * batch * variants / (ms / n * 1e-3) / 1e9, 1)
+
+    value = world * frames * args.steps / (ms_total * 1e-3)
+    e2e = world * frames * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "rtf": sec_step / (frames * HOP / SR), "x_realtime": (frames * HOP / SR) / sec_step,
+        "config": {"workload": f"{cfg.name}: batch {batch}/GPU, ref {cfg.ref_frames} frames, N {cfg.total_frames}, "
+                               f"{cfg.n_text} phones, NFE {cfg.steps}, cfg {cfg.cfg_strength}, sway {cfg.sway_coef}; "
+                               "full 336M-param DiT (22 layers) + Vocos, random-init weights",
+                   "step": "CFM.sample (64 co-batched DiT forwards) + Vocos.decode of one utterance batch per GPU",
+                   "l2": "256 MiB buffer written between timed iterations; per-step working set (0.7 GB weights) > L2",
+                   "parallelism": f"utterance sharding x{world}, one weight broadcast, no per-step collective"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": world * (cond_h.numel() * 4 + text_h.numel() * 8),
+                "d2h_bytes_per_step": world * wav_h.numel() * 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "attention_kernel (tcgen05, csrc/attention.cu)",
+                     "achieved": att_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": att_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
+                     "flops_per_launch": att_flops, "launch_ms": att_ms / att_n if att_n else None},
+        "sampler_tensor_frac": dit_flops / sec_step / 1e12 / pk["tflops"],
+        "kernels": kinds, "profiled_step_ms": prof_ms,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        info = cpu_oracle_sample(cfg, batch, euler_steps=1)
+        line["cpu_baseline"] = {"value": frames / info["seconds"], "unit": UNIT, "cores": info["cores"],
+                                "kind": "port", "sample": info["sample"],
+                                "seconds_per_step_scaled": info["seconds"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,11 @@ const char* lemas_last_error(void);
 int lemas_version(void);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMA kernels can run), else 0. */
 int lemas_device_supported(void);
+/* sizeof() of the ABI structs, for bindings to self-check their mirrors: 0 lemas_gemm_desc, 1 lemas_dit_config,
+ * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights; else -1. */
+int lemas_abi_sizeof(int which);
+/* Number of kernels this library has launched in the calling process since it was loaded (all entry points). */
+int64_t lemas_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Op-level entry points (one kernel launch each).  Used by the engine below and by the op-level parity tests.
@@ -186,6 +191,27 @@ typedef struct lemas_sample_args {
 
 /* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */
 int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream);
+
+/* Per-kernel-kind device timing of the sampler (measurement aid, off by default).  When enabled every launch issued
+ * by lemas_sampler_run / lemas_dit_forward is bracketed by CUDA events on the launching stream.
+ * lemas_engine_profile_read synchronises the stream, adds the elapsed times since the last read to ms[kind] and
+ * launches[kind] (arrays of LEMAS_PROF_KINDS entries) and clears the record. */
+enum lemas_prof_kind {
+  LEMAS_PROF_PRELOOP = 0,   /* time MLP, AdaLN table, packing, step-invariant input projection */
+  LEMAS_PROF_IN_PROJ = 1,   /* dit.py:97 x-columns GEMM                                         */
+  LEMAS_PROF_CONV_POS = 2,  /* modules.py:171-176 grouped conv k31 + Mish (2 launches / forward)*/
+  LEMAS_PROF_LN_MOD = 3,    /* LayerNorm + AdaLN modulate                                       */
+  LEMAS_PROF_GEMM_QKV = 4,
+  LEMAS_PROF_ATTENTION = 5,
+  LEMAS_PROF_GEMM_OUT = 6,
+  LEMAS_PROF_GEMM_FF1 = 7,
+  LEMAS_PROF_GEMM_FF2 = 8,
+  LEMAS_PROF_PROJ_OUT = 9,
+  LEMAS_PROF_CFG_EULER = 10,
+  LEMAS_PROF_KINDS = 11
+};
+int lemas_engine_profile(lemas_engine* e, int32_t enable);
+int lemas_engine_profile_read(lemas_engine* e, double* ms, int64_t* launches, void* stream);
 
 /* One DiT.forward (dit.py:194-254) on the co-batched cond/uncond rows; pred: fp32 [2*batch*seq, 128]. Testing aid. */
 int lemas_dit_forward(lemas_engine* e, const lemas_sample_args* a, float t, float* pred, float* hidden_out,

@@ -302,6 +302,6 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   p.inner = inner;
   dim3 grid((seq + ATT_BM - 1) / ATT_BM, heads, batch);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQK, tmVT, p);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

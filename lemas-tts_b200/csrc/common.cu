@@ -1,5 +1,6 @@
 #include "common.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace lemas {
@@ -11,6 +12,9 @@ int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
 }
+
+static std::atomic<int64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
   static int n = 0;
@@ -75,6 +79,21 @@ extern "C" {
 
 const char* lemas_last_error(void) { return lemas::g_last_error.c_str(); }
 int lemas_version(void) { return 100; }
+
+int64_t lemas_launch_count(void) { return lemas::g_launches.load(); }
+
+int lemas_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(lemas_gemm_desc);
+    case 1: return (int)sizeof(lemas_dit_config);
+    case 2: return (int)sizeof(lemas_dit_layer);
+    case 3: return (int)sizeof(lemas_dit_weights);
+    case 4: return (int)sizeof(lemas_sample_args);
+    case 5: return (int)sizeof(lemas_vocos_layer);
+    case 6: return (int)sizeof(lemas_vocos_weights);
+  }
+  return -1;
+}
 
 int lemas_device_supported(void) {
   int n = 0;

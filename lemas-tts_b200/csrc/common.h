@@ -13,6 +13,7 @@ namespace lemas {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 int sm_count();
+void count_launches(int n);
 
 #define LEMAS_CUDA_OK(expr)                                                                          \
   do {                                                                                               \
@@ -20,6 +21,13 @@ int sm_count();
     if (_e != cudaSuccess)                                                                           \
       return ::lemas::fail(LEMAS_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) +    \
                                                " at " __FILE__ ":" + std::to_string(__LINE__));      \
+  } while (0)
+
+// after a kernel launch: surface launch errors and account the launch (lemas_launch_count)
+#define LEMAS_LAUNCHED(n)                    \
+  do {                                       \
+    LEMAS_CUDA_OK(cudaGetLastError());       \
+    ::lemas::count_launches(n);              \
   } while (0)
 
 #define LEMAS_REQUIRE(cond, msg)                                                   \

@@ -331,7 +331,7 @@ int lemas_ln_modulate(const float* x, const float* scale, const float* shift, in
   LEMAS_REQUIRE(rows > 0 && seq_len > 0, "lemas_ln_modulate: bad shape");
   ln_kernel<false><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, mod_bstride, (__half*)out16,
                                                                      nullptr, rows, dim, seq_len, 1e-6f);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -340,7 +340,7 @@ int lemas_ln_affine(const float* x, const float* weight, const float* bias, void
   LEMAS_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_VEC, "lemas_ln_affine: dim must be a multiple of 128, <= 1024");
   ln_kernel<true><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, 0, (__half*)out16, out32, rows,
                                                                     dim, 1 << 30, eps);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -362,13 +362,13 @@ int lemas_skinny_linear_f32(const float* x, const float* w, const float* b, floa
     skinny_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x + (long)m0 * k, w, b, y + (long)m0 * n, mm, k, n,
                                                                     act_in, act_out);
   }
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED((m + 31) / 32);
   return LEMAS_OK;
 }
 
 int lemas_time_sinusoid(const float* t, float* out, int32_t m, void* stream) {
   time_sinusoid_kernel<<<(m * 128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, out, m);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -380,7 +380,7 @@ int lemas_pack_cond_text(const float* cond, const float* text_c, const float* te
   if (grid > sm_count() * 16) grid = sm_count() * 16;
   pack_cond_text_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cond, text_c, text_u, (__half*)out16, rows, mel,
                                                                text_dim, ld, n_variants);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -391,7 +391,7 @@ int lemas_cast_pad_f16(const float* x, void* out16, int32_t rows, int32_t cols, 
   int grid = (int)((per + 255) / 256);
   if (grid > sm_count() * 16) grid = sm_count() * 16;
   cast_pad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__half*)out16, rows, cols, ld, copies);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -404,7 +404,7 @@ int lemas_cfg_euler(const float* pred, int32_t ld_pred, float* y, void* x16, int
   cfg_euler_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pred, ld_pred, y, (__half*)x16, ld_x16,
                                                                                copies, traj_out, rows, mel, cfg_t,
                                                                                use_cfg, dt);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -414,7 +414,7 @@ int lemas_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const
   const int rows = batch * t;
   dwconv7_ln_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, dw_w, dw_b, ln_w, ln_b, (__half*)out16, batch,
                                                                       t, dim);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 
@@ -424,7 +424,7 @@ int lemas_istft_1024(const float* head, int32_t ld_head, float* frames_ws, float
   istft_frames_kernel<<<batch * t, 256, 0, (cudaStream_t)stream>>>(head, ld_head, frames_ws);
   const long total = (long)batch * (t - 1) * HOP;
   istft_ola_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(frames_ws, wav, batch, t);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(2);
   return LEMAS_OK;
 }
 }

@@ -64,11 +64,30 @@ static DitBuffers carve(const lemas_dit_config& c, int batch, int seq, int steps
 
 using namespace lemas;
 
+struct ProfRecord { int kind; cudaEvent_t e0, e1; };
+
 struct lemas_engine {
   lemas_dit_config cfg;
   lemas_dit_weights w;
   std::vector<lemas_dit_layer> layers;
+  bool profile = false;
+  std::vector<ProfRecord> records;     // event pairs in flight since the last profile_read
+  std::vector<cudaEvent_t> free_events;
 };
+
+// Brackets one launch with events when profiling is on (lemas_engine_profile); otherwise free.
+struct ProfScope {
+  lemas_engine* e; cudaStream_t st; ProfRecord r; bool on;
+  ProfScope(const lemas_engine* ce, int kind, cudaStream_t s) : e(const_cast<lemas_engine*>(ce)), st(s), on(ce->profile) {
+    if (!on) return;
+    auto get = [&]() { cudaEvent_t ev; if (!e->free_events.empty()) { ev = e->free_events.back(); e->free_events.pop_back(); }
+                       else cudaEventCreate(&ev); return ev; };
+    r.kind = kind; r.e0 = get(); r.e1 = get();
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.e1, st); e->records.push_back(r); } }
+};
+#define PROF(kind) ProfScope _prof_scope_##__LINE__(e, kind, st)
 
 static int ct_ld_for(const lemas_dit_config* c) { return (int)align_up(c->mel_dim + c->text_dim, 64); }
 
@@ -99,7 +118,32 @@ int lemas_engine_create(const lemas_dit_config* cfg, const lemas_dit_weights* w,
   return LEMAS_OK;
 }
 
-void lemas_engine_destroy(lemas_engine* e) { delete e; }
+void lemas_engine_destroy(lemas_engine* e) {
+  if (!e) return;
+  for (auto& r : e->records) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto ev : e->free_events) cudaEventDestroy(ev);
+  delete e;
+}
+
+int lemas_engine_profile(lemas_engine* e, int32_t enable) {
+  LEMAS_REQUIRE(e, "lemas_engine_profile: null engine");
+  e->profile = enable != 0;
+  return LEMAS_OK;
+}
+
+int lemas_engine_profile_read(lemas_engine* e, double* ms, int64_t* launches, void* stream) {
+  LEMAS_REQUIRE(e && ms && launches, "lemas_engine_profile_read: null argument");
+  LEMAS_CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  for (auto& r : e->records) {
+    float t = 0.f;
+    LEMAS_CUDA_OK(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (r.kind >= 0 && r.kind < LEMAS_PROF_KINDS) { ms[r.kind] += t; launches[r.kind] += 1; }
+    e->free_events.push_back(r.e0);
+    e->free_events.push_back(r.e1);
+  }
+  e->records.clear();
+  return LEMAS_OK;
+}
 }
 
 namespace lemas {
@@ -127,6 +171,7 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
   {  // dit.py:97  x-columns of the input projection + the precomputed (cond|text) part
     lemas_gemm_desc d = base_desc(b.x16, 1, M, 128, w.w_in_x, D, 128, D, seq, LEMAS_EPI_ADD_F32_F16, bn_d);
     d.resid = b.inv_embed; d.ldr = D; d.out32 = b.h0; d.ld32 = D; d.out16 = b.h0_16; d.ld16 = D;
+    PROF(LEMAS_PROF_IN_PROJ);
     LEMAS_TRY(gemm_launch(d, st));
   }
   for (int j = 0; j < 2; ++j) {  // modules.py:171-176 grouped conv k=31 + Mish, twice; dit.py:98 residual
@@ -139,42 +184,51 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
     d.bias = w.conv_b[j]; d.seq_len = seq;
     if (j == 0) { d.epilogue = LEMAS_EPI_MISH_F16; d.out16 = b.c1_16; d.ld16 = D; }
     else { d.epilogue = LEMAS_EPI_MISH_RESID_F32; d.resid = b.h0; d.ldr = D; d.out32 = b.x; d.ld32 = D; }
+    PROF(LEMAS_PROF_CONV_POS);
     LEMAS_TRY(gemm_launch(d, st));
   }
   for (int l = 0; l < c.depth; ++l) {
     const lemas_dit_layer& L = w.layers[l];
     const float* m = mod + (int64_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    LEMAS_TRY(lemas_ln_modulate(b.x, m + D, m, 0, b.a16, M, D, seq, st));
+    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, m + D, m, 0, b.a16, M, D, seq, st)); }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_qkv, 3 * inner, D, 3 * inner, seq, LEMAS_EPI_QKV_ROPE, 256);
       d.bias = L.b_qkv; d.out16 = b.qk16; d.ld16 = 2 * inner; d.rope = rope;
       d.rope_cols = c.rope_heads * 64; d.inner = inner; d.vt = b.vt16; d.vt_ld = b.npad;
+      PROF(LEMAS_PROF_GEMM_QKV);
       LEMAS_TRY(gemm_launch(d, st));
     }
-    LEMAS_TRY(lemas_attention_f16(b.qk16, 2 * inner, b.vt16, b.npad, kv_len2, b.o16, B2, seq, c.heads, st));
+    {
+      PROF(LEMAS_PROF_ATTENTION);
+      LEMAS_TRY(lemas_attention_f16(b.qk16, 2 * inner, b.vt16, b.npad, kv_len2, b.o16, B2, seq, c.heads, st));
+    }
     {
       lemas_gemm_desc d = base_desc(b.o16, 1, M, inner, L.w_out, D, inner, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
       d.bias = L.b_out; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 2 * D; d.gate_bstride = 0;
       d.row_valid = kv_len2;
+      PROF(LEMAS_PROF_GEMM_OUT);
       LEMAS_TRY(gemm_launch(d, st));
     }
-    LEMAS_TRY(lemas_ln_modulate(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, st));
+    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, st)); }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_ff1, F, D, F, seq, LEMAS_EPI_GELU_TANH_F16, 256);
       d.bias = L.b_ff1; d.out16 = b.ff16; d.ld16 = F;
+      PROF(LEMAS_PROF_GEMM_FF1);
       LEMAS_TRY(gemm_launch(d, st));
     }
     {
       lemas_gemm_desc d = base_desc(b.ff16, 1, M, F, L.w_ff2, D, F, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
       d.bias = L.b_ff2; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 5 * D; d.gate_bstride = 0;
+      PROF(LEMAS_PROF_GEMM_FF2);
       LEMAS_TRY(gemm_launch(d, st));
     }
   }
   const float* mf = mod + (int64_t)c.depth * 6 * D;  // modules.py:333: (scale, shift)
-  LEMAS_TRY(lemas_ln_modulate(b.x, mf, mf + D, 0, b.a16, M, D, seq, st));
+  { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, mf, mf + D, 0, b.a16, M, D, seq, st)); }
   {
     lemas_gemm_desc d = base_desc(b.a16, 1, M, D, w.w_proj, 128, D, c.mel_dim, seq, LEMAS_EPI_BIAS_F32, 128);
     d.bias = w.b_proj; d.out32 = pred; d.ld32 = 128;
+    PROF(LEMAS_PROF_PROJ_OUT);
     LEMAS_TRY(gemm_launch(d, st));
   }
   return LEMAS_OK;
@@ -189,6 +243,7 @@ static int prepare(const lemas_engine* e, const DitBuffers& b, const lemas_sampl
   const int D = c.dim;
   const int rows = a->batch * a->seq;
   const int64_t mod_w = (int64_t)c.depth * 6 * D + 2 * D;
+  PROF(LEMAS_PROF_PRELOOP);
   LEMAS_CUDA_OK(cudaMemcpyAsync(b.t_dev, times_host, sizeof(float) * n_times, cudaMemcpyHostToDevice, st));
   LEMAS_TRY(lemas_time_sinusoid(b.t_dev, b.sinus, n_times, st));
   LEMAS_TRY(lemas_skinny_linear_f32(b.sinus, w.time_w0, w.time_b0, b.t1, n_times, 256, D, 0, 1, st));
@@ -246,6 +301,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
     const float t = a->t_grid_host[i];
     const float dt = a->t_grid_host[i + 1] - t;
     float* traj = a->trajectory ? a->trajectory + (int64_t)(i + 1) * state : nullptr;
+    PROF(LEMAS_PROF_CFG_EULER);
     LEMAS_TRY(lemas_cfg_euler(b.pred, 128, a->y, b.x16, 128, variants, traj, rows, c.mel_dim, t, dt,
                               variants == 2 ? a->cfg_strength : 0.f, st));
   }
@@ -334,7 +390,7 @@ int lemas_vocos_decode(const lemas_vocos_weights* w, const float* mel, float* wa
     int grid = (int)((total + 255) / 256);
     if (grid > sm_count() * 16) grid = sm_count() * 16;
     mel_to_rows_kernel<<<grid, 256, 0, st>>>(mel, b.mel16, batch, w->in_ch, t);
-    LEMAS_CUDA_OK(cudaGetLastError());
+    LEMAS_LAUNCHED(1);
   }
   {  // backbone.embed: Conv1d(in_ch -> dim, k=7, pad=3) as a 7-tap GEMM
     lemas_gemm_desc d = {};

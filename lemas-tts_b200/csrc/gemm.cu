@@ -330,7 +330,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmPara
   const int cap = max_ctas > 0 ? max_ctas : sm_count();
   if (grid > cap) grid = cap;
   kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmW, p);
-  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 

@@ -19,6 +19,8 @@ _lib = None
 
 EPI_BIAS_F16, EPI_QKV_ROPE, EPI_GELU_TANH_F16, EPI_GELU_ERF_F16, EPI_GATE_RESID_F32 = 0, 1, 2, 3, 4
 EPI_BIAS_F32, EPI_ADD_F32_F16, EPI_MISH_F16, EPI_MISH_RESID_F32 = 5, 6, 7, 8
+PROF_KINDS = ["preloop", "in_proj", "conv_pos", "ln_mod", "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
+              "proj_out", "cfg_euler"]
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
@@ -77,6 +79,10 @@ SIGNATURES = {
     "lemas_last_error": (C.c_char_p, []),
     "lemas_version": (C.c_int, []),
     "lemas_device_supported": (C.c_int, []),
+    "lemas_abi_sizeof": (C.c_int, [C.c_int]),
+    "lemas_launch_count": (i64, []),
+    "lemas_engine_profile": (C.c_int, [vp, i32]),
+    "lemas_engine_profile_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), vp]),
     "lemas_gemm_f16": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "lemas_ln_modulate": (C.c_int, [vp, vp, vp, i32, vp, i32, i32, i32, vp]),
     "lemas_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),

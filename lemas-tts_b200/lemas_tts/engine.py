@@ -1,0 +1,289 @@
+"""Host side of the native engine: packs reference-layout weights into the buffers liblemas_b200.so reads
+and drives `lemas_sampler_run` / `lemas_dit_forward` / `lemas_vocos_decode` (include/lemas_b200.h).
+
+Pure plumbing: torch owns the device memory and the stream, the library does every FLOP.  There is no fallback:
+a missing library or a non-Blackwell device raises RuntimeError("CUDA error: ...") from `_native`.
+
+Weight layout (reference checkpoint keys -> engine buffers):
+  transformer.time_embed.time_mlp.{0,2}                       -> fp32 time_w0/time_w2 (pre-loop skinny GEMMs)
+  transformer_blocks.{i}.attn_norm.linear, norm_out.linear    -> ONE stacked fp32 [depth*6*D + 2*D, D] matrix:
+                                                                 all AdaLN modulations of all steps are produced
+                                                                 before the ODE loop (they depend on t only)
+  input_embed.proj  [D, mel | mel | text]                     -> fp16 x-columns [D,128] + fp16 (cond|text) columns
+  input_embed.conv_pos_embed.conv1d.{0,2}  [D, D/16, 31]      -> fp16 tap-major [31*D, 64] (grouped, D/16 == 64) or
+                                                                 block-diagonal dense [31*D, D]
+  attn.to_q | to_k | to_v                                     -> fp16 [3*inner, D] stacked, fp32 bias
+  attn.to_out.0, ff.ff.0.0, ff.ff.2, proj_out                 -> fp16, fp32 bias
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _native as nv
+
+f16, f32 = torch.float16, torch.float32
+
+
+def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=dtype).contiguous()
+
+
+class DiTEngine:
+    """Owns the packed DiT weights on one device and a native engine handle."""
+
+    def __init__(self, sd: dict, *, dim: int, depth: int, heads: int, ff_mult: int, text_dim: int, mel_dim: int,
+                 pe_attn_head: int | None = None, qk_norm: str | None = None, device="cuda",
+                 prefix: str = "transformer."):
+        nv.require_device()
+        if qk_norm is not None:
+            raise RuntimeError("lemas_b200 error: qk_norm is not supported by the sm_100a engine "
+                               "(both shipped configs set qk_norm: null)")
+        self.device = torch.device(device)
+        self.dim, self.depth, self.heads, self.ff_mult = dim, depth, heads, ff_mult
+        self.text_dim, self.mel_dim = text_dim, mel_dim
+        self.inner = heads * 64
+        self.rope_heads = heads if pe_attn_head is None else int(pe_attn_head)
+        D, M, Dt, dv = dim, mel_dim, text_dim, self.device
+        p = prefix
+        keep = self._keep = []  # every tensor the native side holds a pointer to
+
+        def hold(t):
+            keep.append(t)
+            return t
+
+        w = nv.DitWeights()
+        w.time_w0 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.0.weight"], dv, f32)))
+        w.time_b0 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.0.bias"], dv, f32)))
+        w.time_w2 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.2.weight"], dv, f32)))
+        w.time_b2 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.2.bias"], dv, f32)))
+        ada_w = [sd[f"{p}transformer_blocks.{i}.attn_norm.linear.weight"] for i in range(depth)]
+        ada_b = [sd[f"{p}transformer_blocks.{i}.attn_norm.linear.bias"] for i in range(depth)]
+        ada_w.append(sd[p + "norm_out.linear.weight"])
+        ada_b.append(sd[p + "norm_out.linear.bias"])
+        w.adaln_w = nv.ptr(hold(_dev(torch.cat([t.float() for t in ada_w], 0), dv, f32)))
+        w.adaln_b = nv.ptr(hold(_dev(torch.cat([t.float() for t in ada_b], 0), dv, f32)))
+
+        proj = sd[p + "input_embed.proj.weight"].float()  # [D, 2*mel + text_dim]: columns x | cond | text
+        assert proj.shape == (D, 2 * M + Dt), proj.shape
+        self.ct_ld = (M + Dt + 63) // 64 * 64
+        w_x = torch.zeros(D, 128)
+        w_x[:, :M] = proj[:, :M]
+        w_ct = torch.zeros(D, self.ct_ld)
+        w_ct[:, : M + Dt] = proj[:, M:]
+        w.w_in_x = nv.ptr(hold(_dev(w_x, dv, f16)))
+        w.w_in_ct = nv.ptr(hold(_dev(w_ct, dv, f16)))
+        w.b_in = nv.ptr(hold(_dev(sd[p + "input_embed.proj.bias"], dv, f32)))
+        w.ct_ld = self.ct_ld
+
+        groups = 16
+        gc = D // groups
+        w.conv_dense = 0 if gc == 64 else 1
+        for j, idx in enumerate((0, 2)):
+            cw = sd[f"{p}input_embed.conv_pos_embed.conv1d.{idx}.weight"].float()  # [D, D/16, 31]
+            taps = cw.shape[-1]
+            assert cw.shape == (D, gc, 31), cw.shape
+            if gc == 64:
+                packed = cw.permute(2, 0, 1).reshape(taps * D, gc)
+            else:  # block-diagonal dense: out channel o reads input channels of its own group only
+                dense = torch.zeros(taps, D, D)
+                for g in range(groups):
+                    dense[:, g * gc:(g + 1) * gc, g * gc:(g + 1) * gc] = cw[g * gc:(g + 1) * gc].permute(2, 0, 1)
+                packed = dense.reshape(taps * D, D)
+            w.conv_w[j] = nv.ptr(hold(_dev(packed, dv, f16)))
+            w.conv_b[j] = nv.ptr(hold(_dev(sd[f"{p}input_embed.conv_pos_embed.conv1d.{idx}.bias"], dv, f32)))
+
+        w_proj = torch.zeros(128, D)
+        w_proj[:M] = sd[p + "proj_out.weight"].float()
+        w.w_proj = nv.ptr(hold(_dev(w_proj, dv, f16)))
+        w.b_proj = nv.ptr(hold(_dev(sd[p + "proj_out.bias"], dv, f32)))
+
+        layers = (nv.DitLayer * depth)()
+        for i in range(depth):
+            q = f"{p}transformer_blocks.{i}."
+            wqkv = torch.cat([sd[q + f"attn.to_{n}.weight"].float() for n in "qkv"], 0)
+            bqkv = torch.cat([sd[q + f"attn.to_{n}.bias"].float() for n in "qkv"], 0)
+            L = layers[i]
+            L.w_qkv, L.b_qkv = nv.ptr(hold(_dev(wqkv, dv, f16))), nv.ptr(hold(_dev(bqkv, dv, f32)))
+            L.w_out = nv.ptr(hold(_dev(sd[q + "attn.to_out.0.weight"], dv, f16)))
+            L.b_out = nv.ptr(hold(_dev(sd[q + "attn.to_out.0.bias"], dv, f32)))
+            L.w_ff1 = nv.ptr(hold(_dev(sd[q + "ff.ff.0.0.weight"], dv, f16)))
+            L.b_ff1 = nv.ptr(hold(_dev(sd[q + "ff.ff.0.0.bias"], dv, f32)))
+            L.w_ff2 = nv.ptr(hold(_dev(sd[q + "ff.ff.2.weight"], dv, f16)))
+            L.b_ff2 = nv.ptr(hold(_dev(sd[q + "ff.ff.2.bias"], dv, f32)))
+        self._layers = layers
+        w.layers = layers
+        self._weights = w
+
+        cfg = nv.DitConfig(dim, depth, heads, ff_mult, text_dim, mel_dim, self.rope_heads)
+        self._cfg = cfg
+        handle = nv.vp()
+        nv.check(nv.load().lemas_engine_create(C.byref(cfg), C.byref(w), C.byref(handle)))
+        self._handle = handle
+
+        # RotaryEmbedding.forward_from_seq_len (x-transformers): angle[n, j] = n * inv_freq[j]; (cos, sin) pairs.
+        inv_freq = sd.get(p + "rotary_embed.inv_freq")
+        if inv_freq is None:
+            inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+        ang = torch.outer(torch.arange(4096, dtype=f32), inv_freq.detach().float().cpu())
+        self._rope = torch.stack((ang.cos(), ang.sin()), dim=-1).to(dv).contiguous()  # [4096, 32, 2]
+        self._ws = None
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h:
+            try:
+                nv.load().lemas_engine_destroy(h)
+            except Exception:
+                pass
+            self._handle = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _workspace(self, batch: int, seq: int, steps: int) -> torch.Tensor:
+        need = int(nv.load().lemas_engine_workspace_bytes(C.byref(self._cfg), batch, seq, steps))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def _args(self, y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength, traj, use_graph):
+        B, N, M = y.shape
+        for name, t, shape in (("y", y, (B, N, self.mel_dim)), ("step_cond", step_cond, (B, N, self.mel_dim)),
+                               ("text_cond", text_c, (B, N, self.text_dim))):
+            if tuple(t.shape) != shape or t.dtype != f32 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError(f"{name}: expected contiguous CUDA fp32 {shape}, got {tuple(t.shape)} {t.dtype}")
+        if text_u is not None and (tuple(text_u.shape) != (B, N, self.text_dim) or text_u.dtype != f32
+                                   or not text_u.is_contiguous()):
+            raise ValueError("text_uncond: bad shape/dtype")
+        if kv_len is not None and (kv_len.dtype != torch.int32 or kv_len.numel() != B or not kv_len.is_cuda):
+            raise ValueError("kv_len: expected CUDA int32 [batch]")
+        if N > 4096:
+            raise ValueError("sequence longer than 4096 frames (cfm.py:218 max_duration)")
+        ws = self._workspace(B, N, max(steps, 1))
+        a = nv.SampleArgs()
+        a.batch, a.seq, a.steps = B, N, steps
+        a.t_grid_host = t_host
+        a.cfg_strength = float(cfg_strength)
+        a.y, a.step_cond = nv.ptr(y), nv.ptr(step_cond)
+        a.text_cond, a.text_uncond = nv.ptr(text_c), nv.ptr(text_u)
+        a.kv_len = nv.ptr(kv_len)
+        a.rope = nv.ptr(self._rope)
+        a.trajectory = nv.ptr(traj)
+        a.workspace, a.workspace_bytes = nv.ptr(ws), ws.numel()
+        a.use_graph = int(use_graph)
+        return a
+
+    def sample_loop(self, y: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor | None,
+                    t_grid: torch.Tensor, cfg_strength: float, kv_len: torch.Tensor | None = None,
+                    trajectory: torch.Tensor | None = None, use_graph: bool = True) -> torch.Tensor:
+        """The ODE loop of CFM.sample (cfm.py:382-456).  `y` [B,N,mel] fp32 is y0 on entry and is updated IN PLACE
+        to the final state.  t_grid: [steps+1] fp32 (any device; read on the host, cfm.py:445-453)."""
+        tg = t_grid.detach().to("cpu", f32).contiguous()
+        steps = tg.numel() - 1
+        t_host = (C.c_float * (steps + 1))(*tg.tolist())
+        a = self._args(y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength, trajectory, use_graph)
+        nv.check(nv.load().lemas_sampler_run(self._handle, C.byref(a), nv.stream()))
+        return y
+
+    def profile(self, enable: bool) -> None:
+        """Bracket every sampler launch with CUDA events (measurement aid, see lemas_engine_profile)."""
+        nv.check(nv.load().lemas_engine_profile(self._handle, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kind: (milliseconds, launches)} accumulated since the last read; synchronises the current stream."""
+        n = len(nv.PROF_KINDS)
+        ms, cnt = (C.c_double * n)(), (C.c_int64 * n)()
+        nv.check(nv.load().lemas_engine_profile_read(self._handle, ms, cnt, nv.stream()))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(nv.PROF_KINDS)}
+
+    def forward_pair(self, x: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor,
+                     t: float, kv_len: torch.Tensor | None = None, want_hidden: bool = False):
+        """One DiT.forward (dit.py:194-254) for the conditional and the unconditional variant at once.
+        Returns (pred_cond, pred_uncond[, hidden]) with pred [B,N,mel] fp32."""
+        B, N, M = x.shape
+        t_host = (C.c_float * 2)(float(t), float(t))
+        a = self._args(x, step_cond, text_c, text_u, kv_len, 1, t_host, 1.0, None, False)
+        pred = torch.empty(2, B, N, 128, device=self.device, dtype=f32)
+        hidden = torch.empty(2, B, N, self.dim, device=self.device, dtype=f32) if want_hidden else None
+        nv.check(nv.load().lemas_dit_forward(self._handle, C.byref(a), float(t), nv.ptr(pred), nv.ptr(hidden),
+                                             nv.stream()))
+        out = (pred[0, ..., :M].contiguous(), pred[1, ..., :M].contiguous())
+        return out + (hidden,) if want_hidden else out
+
+
+class VocosEngine:
+    """Packed Vocos (charactr/vocos-mel-24khz layout) weights + `lemas_vocos_decode`."""
+
+    def __init__(self, sd: dict, device="cuda"):
+        nv.require_device()
+        self.device = dv = torch.device(device)
+        keep = self._keep = []
+
+        def hold(t):
+            keep.append(t)
+            return t
+
+        emb = sd["backbone.embed.weight"].float()  # [dim, in_ch, 7]
+        dim, in_ch, k = emb.shape
+        assert k == 7 and in_ch <= 128
+        n_layers = 0
+        while f"backbone.convnext.{n_layers}.dwconv.weight" in sd:
+            n_layers += 1
+        inter = sd["backbone.convnext.0.pwconv1.weight"].shape[0]
+        head = sd["head.out.weight"].float()
+        if head.shape[0] != 1026:
+            raise RuntimeError("lemas_b200 error: the sm_100a ISTFT head is built for n_fft=1024 (head.out rows 1026)")
+        win = sd.get("head.istft.window")
+        if win is not None and not torch.allclose(win.float().cpu(), torch.hann_window(1024), atol=1e-6):
+            raise RuntimeError("lemas_b200 error: head.istft.window is not the periodic hann window")
+        self.dim, self.inter, self.layers, self.in_ch = dim, inter, n_layers, in_ch
+        w = nv.VocosWeights()
+        w.dim, w.inter, w.layers, w.in_ch = dim, inter, n_layers, in_ch
+        e = torch.zeros(7, dim, 128)
+        e[..., :in_ch] = emb.permute(2, 0, 1)
+        w.embed_w = nv.ptr(hold(_dev(e.reshape(7 * dim, 128), dv, f16)))
+        w.embed_b = nv.ptr(hold(_dev(sd["backbone.embed.bias"], dv, f32)))
+        w.norm_w = nv.ptr(hold(_dev(sd["backbone.norm.weight"], dv, f32)))
+        w.norm_b = nv.ptr(hold(_dev(sd["backbone.norm.bias"], dv, f32)))
+        blocks = (nv.VocosLayer * n_layers)()
+        for i in range(n_layers):
+            q = f"backbone.convnext.{i}."
+            L = blocks[i]
+            L.dw_w = nv.ptr(hold(_dev(sd[q + "dwconv.weight"].float()[:, 0].t(), dv, f32)))  # [7, dim]
+            L.dw_b = nv.ptr(hold(_dev(sd[q + "dwconv.bias"], dv, f32)))
+            L.ln_w = nv.ptr(hold(_dev(sd[q + "norm.weight"], dv, f32)))
+            L.ln_b = nv.ptr(hold(_dev(sd[q + "norm.bias"], dv, f32)))
+            L.w1 = nv.ptr(hold(_dev(sd[q + "pwconv1.weight"], dv, f16)))
+            L.b1 = nv.ptr(hold(_dev(sd[q + "pwconv1.bias"], dv, f32)))
+            L.w2 = nv.ptr(hold(_dev(sd[q + "pwconv2.weight"], dv, f16)))
+            L.b2 = nv.ptr(hold(_dev(sd[q + "pwconv2.bias"], dv, f32)))
+            L.gamma = nv.ptr(hold(_dev(sd[q + "gamma"], dv, f32)))
+        self._blocks = blocks
+        w.blocks = blocks
+        w.final_w = nv.ptr(hold(_dev(sd["backbone.final_layer_norm.weight"], dv, f32)))
+        w.final_b = nv.ptr(hold(_dev(sd["backbone.final_layer_norm.bias"], dv, f32)))
+        hw = torch.zeros(1152, dim)
+        hw[:1026] = head
+        w.head_w = nv.ptr(hold(_dev(hw, dv, f16)))
+        w.head_b = nv.ptr(hold(_dev(sd["head.out.bias"], dv, f32)))
+        self._weights = w
+        self._ws = None
+
+    def decode(self, mel: torch.Tensor) -> torch.Tensor:
+        """Vocos.decode (utils_infer.py:549): mel [B, in_ch, T] -> wav [B, (T-1)*256] fp32."""
+        if mel.dim() != 3 or mel.shape[1] != self.in_ch:
+            raise ValueError(f"mel: expected [B, {self.in_ch}, T], got {tuple(mel.shape)}")
+        mel = mel.to(device=self.device, dtype=f32).contiguous()
+        B, _, T = mel.shape
+        if T < 2:
+            raise ValueError("vocos decode needs at least 2 frames")
+        need = int(nv.load().lemas_vocos_workspace_bytes(C.byref(self._weights), B, T))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        wav = torch.empty(B, (T - 1) * 256, device=self.device, dtype=f32)
+        nv.check(nv.load().lemas_vocos_decode(C.byref(self._weights), nv.ptr(mel), nv.ptr(wav), B, T,
+                                              nv.ptr(self._ws), self._ws.numel(), nv.stream()))
+        return wav

@@ -1,0 +1,120 @@
+"""CPU checks of the host side that mirrors the reference interface: checkpoint key layout, time grid, text embedding
+(torch plumbing) against the oracle / golden vectors, tokenizer and chunking helpers, cross-fade."""
+import numpy as np
+import pytest
+import torch
+
+import golden_cases as gc
+from lemas_tts import synthetic as syn
+
+
+def _cfm(arch):
+    from lemas_tts.model.backbones.dit import DiT
+    from lemas_tts.model.cfm import CFM
+
+    return CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"))
+
+
+def test_state_dict_key_set_is_the_reference_layout():
+    model = _cfm(syn.FULL_ARCH)
+    sd = syn.make_dit_state_dict(syn.FULL_ARCH, seed=0)
+    assert len(sd) == 368  # 368 tensors for the grl model
+    model.load_state_dict(sd, strict=True)
+    assert abs(sum(p.numel() for p in model.parameters()) - 336.37e6) < 0.01e6
+    with pytest.raises(RuntimeError):
+        bad = dict(sd)
+        bad.pop("transformer.proj_out.bias")
+        model.load_state_dict(bad, strict=True)
+
+
+def test_time_grid_bit_equal_to_reference():
+    from lemas_tts.model.cfm import sway_time_grid
+
+    grids = torch.load(gc.GOLDEN / "time_grids.pt", weights_only=True)
+    for key, want in grids.items():
+        steps, coef = key.split("_")
+        got = sway_time_grid(int(steps), None if coef == "None" else float(coef))
+        assert torch.equal(got, want), key
+
+
+@pytest.mark.parametrize("drop", [False, True])
+def test_text_embedding_matches_oracle(drop):
+    from oracle import lemas_oracle as orc
+
+    arch = syn.TINY_ARCH
+    sd = syn.make_dit_state_dict(arch, seed=11)
+    model = _cfm(arch)
+    model.load_state_dict(sd, strict=True)
+    text = syn.synthetic_text_ids(3, 40, arch.text_num_embeds, seed=2, lengths=[40, 22, 35])
+    got = model.transformer.text_embed(text, 131, drop_text=drop)
+    want = orc.text_embedding(sd, arch, text, 131, drop_text=drop)
+    assert (got - want).abs().max() < 2e-5
+
+
+def test_load_checkpoint_formats(tmp_path):
+    from safetensors.torch import save_file
+
+    from lemas_tts.infer.utils_infer import load_checkpoint
+
+    arch = syn.TINY_ARCH
+    sd = syn.make_dit_state_dict(arch, seed=3)
+    # safetensors, EMA layout with the bookkeeping and legacy keys the reference strips (utils_infer.py:224-235)
+    ema = {"ema_model." + k: v for k, v in sd.items()}
+    ema["initted"] = torch.tensor(1.0)
+    ema["step"] = torch.tensor(5.0)
+    ema["ema_model.mel_spec.mel_stft.spectrogram.window"] = torch.zeros(4)
+    ema["ema_model.ctc.proj.0.weight"] = torch.zeros(4)
+    p1 = tmp_path / "model.safetensors"
+    save_file({k: v.contiguous() for k, v in ema.items()}, str(p1))
+    m1 = load_checkpoint(_cfm(arch), str(p1), "cpu", use_ema=True)
+    # .pt, non-EMA layout, stored in fp16 like a released CUDA checkpoint
+    p2 = tmp_path / "model.pt"
+    torch.save({"model_state_dict": {k: v.half() if v.is_floating_point() else v for k, v in sd.items()}}, p2)
+    m2 = load_checkpoint(_cfm(arch), str(p2), "cpu", use_ema=False)
+    k = "transformer.transformer_blocks.1.attn.to_q.weight"
+    assert torch.equal(m1.state_dict()[k], sd[k])
+    assert torch.equal(m2.state_dict()[k], sd[k].half().float())
+
+
+def test_tokenizer_and_text_helpers(tmp_path):
+    from lemas_tts.infer.utils_infer import chunk_text, cross_fade_concat
+    from lemas_tts.model.utils import get_tokenizer, lens_to_mask, list_str_to_idx
+
+    vocab = tmp_path / "vocab.txt"
+    vocab.write_text(" \na\nb\n(en)\n")
+    m, n = get_tokenizer(str(vocab), "custom")
+    assert n == 4 and m["(en)"] == 3
+    ids = list_str_to_idx([["(en)", "a", "zzz"], ["b"]], m)
+    assert ids.tolist() == [[3, 1, 0], [2, -1, -1]]
+    assert lens_to_mask(torch.tensor([1, 3])).tolist() == [[True, False, False], [True, True, True]]
+    assert all(len(c.encode()) <= 40 for c in chunk_text("One two three. Four five six, seven! Eight nine ten?", 40))
+    a, b = np.ones(10000), np.zeros(10000)
+    x = cross_fade_concat([a, b], 0.15)
+    assert len(x) == 20000 - 3600 and x[0] == 1 and x[-1] == 0 and 0.49 < x[10000 - 1800] < 0.51
+
+
+def test_process_phone_list():
+    from lemas_tts.api import process_phone_list
+
+    got = process_phone_list(["(en)", "h", "_", ",", "_", "(zh)", "n", "."])
+    assert got == ["(en)h", ",", "(zh)n", "."]
+
+
+def test_vocos_from_hparams(tmp_path):
+    from lemas_tts.vocoder import Vocos
+
+    cfg = tmp_path / "config.yaml"
+    cfg.write_text("""
+feature_extractor:
+  class_path: vocos.feature_extractors.MelSpectrogramFeatures
+  init_args: {sample_rate: 24000, n_fft: 1024, hop_length: 256, n_mels: 100, padding: center}
+backbone:
+  class_path: vocos.models.VocosBackbone
+  init_args: {input_channels: 100, dim: 512, intermediate_dim: 1536, num_layers: 8}
+head:
+  class_path: vocos.heads.ISTFTHead
+  init_args: {dim: 512, n_fft: 1024, hop_length: 256, padding: center}
+""")
+    v = Vocos.from_hparams(str(cfg))
+    v.load_state_dict(syn.make_vocos_state_dict(), strict=True)
+    assert sum(p.numel() for p in v.parameters()) == 13_531_650 or sum(p.numel() for p in v.parameters()) > 13e6
