@@ -16,8 +16,11 @@
 //
 // Replaces the cuBLASLt calls behind nn.Linear / nn.Conv1d on the reference hot path
 // (modules.py:171-176, 349-350, 452-454, 495; dit.py:97, 252) — see include/lemas_b200.h for the epilogues.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
+#include "gemm_params.cuh"
 
 namespace lemas {
 
@@ -25,34 +28,6 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 192;
-
-struct GemmParams {
-  int batches, rows;      // A tiling: tiles never straddle a batch item
-  int n, k_iters, kc_per_tap, tap_pad, w_tap_stride, group_cols;
-  const float* bias;
-  __half* out16; int ld16;
-  float* out32; int ld32;
-  const float* resid; int ldr;
-  const float* gate; int gate_bstride;
-  const int* row_valid;
-  int seq_len;
-  const float2* rope; int rope_cols; int inner;
-  __half* vt; int vt_ld;
-};
-
-DEVI float gelu_tanh_f(float x) {
-  // 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)),  u = sqrt(2/pi) (x + 0.044715 x^3)
-  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  return x / (1.0f + __expf(-2.0f * u));
-}
-DEVI float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
-DEVI float mish_f(float x) {
-  // x * tanh(softplus(x)); tanh(log(1+e^x)) = (n^2 + 2n) / (n^2 + 2n + 2), n = e^x  (softplus threshold 20 as torch)
-  if (x > 20.0f) return x;
-  float n = __expf(x);
-  float a = n * (n + 2.0f);
-  return x * (a / (a + 2.0f));
-}
 
 DEVI void store16x32(__half* dst, const float (&v)[32]) {
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -345,6 +320,19 @@ static int dispatch_bn(int bn, const CUtensorMap& a, const CUtensorMap& w, const
   return fail(LEMAS_ERR_INVALID, "lemas_gemm_f16: block_n must be 64, 128 or 256");
 }
 
+bool gemm2_eligible(const lemas_gemm_desc& d);
+int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p, cudaStream_t st);
+
+// LEMAS_GEMM_PAIR=0 forces the single-CTA kernel everywhere (A/B measurements)
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LEMAS_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   LEMAS_REQUIRE(d.a && d.w, "lemas_gemm_f16: null operand");
   LEMAS_REQUIRE(d.k_per_tap > 0 && d.k_per_tap % BLOCK_K == 0, "lemas_gemm_f16: k_per_tap must be a multiple of 64");
@@ -354,19 +342,6 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
                 "lemas_gemm_f16: operands must be 16-byte aligned");
   LEMAS_REQUIRE(d.seq_len > 0, "lemas_gemm_f16: seq_len must be set");
 
-  CUtensorMap tmA, tmW;
-  {
-    uint64_t dims[3] = {(uint64_t)d.a_cols, (uint64_t)d.rows, (uint64_t)d.batches};
-    uint64_t strides[2] = {(uint64_t)d.lda * 2, (uint64_t)d.rows * d.lda * 2};
-    uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-    LEMAS_TRY(make_tensor_map_f16(&tmA, d.a, 3, dims, strides, box));
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)d.ldw, (uint64_t)d.w_rows};
-    uint64_t strides[1] = {(uint64_t)d.ldw * 2};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)d.block_n};
-    LEMAS_TRY(make_tensor_map_f16(&tmW, d.w, 2, dims, strides, box));
-  }
   GemmParams p;
   p.batches = d.batches; p.rows = d.rows; p.n = d.n;
   p.kc_per_tap = d.k_per_tap / BLOCK_K;
@@ -397,6 +372,22 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   if (d.epilogue == LEMAS_EPI_QKV_ROPE)
     LEMAS_REQUIRE(d.rope && d.vt && d.inner % 64 == 0 && d.n == 3 * d.inner && d.rope_cols % 64 == 0,
                   "lemas_gemm_f16: QKV epilogue needs rope table, vt buffer and n == 3*inner");
+
+  if (pair_enabled() && gemm2_eligible(d)) return gemm2_launch(d, p, stream);
+
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[3] = {(uint64_t)d.a_cols, (uint64_t)d.rows, (uint64_t)d.batches};
+    uint64_t strides[2] = {(uint64_t)d.lda * 2, (uint64_t)d.rows * d.lda * 2};
+    uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+    LEMAS_TRY(make_tensor_map_f16(&tmA, d.a, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d.ldw, (uint64_t)d.w_rows};
+    uint64_t strides[1] = {(uint64_t)d.ldw * 2};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)d.block_n};
+    LEMAS_TRY(make_tensor_map_f16(&tmW, d.w, 2, dims, strides, box));
+  }
 
   switch (d.epilogue) {
     case LEMAS_EPI_BIAS_F16: return dispatch_bn<LEMAS_EPI_BIAS_F16>(d.block_n, tmA, tmW, p, d.max_ctas, stream);

@@ -1,0 +1,341 @@
+// CTA-pair tcgen05 GEMM for sm_100a: 256 x 256 output tiles computed by two CTAs on the two SMs of a TPC
+// (tcgen05.mma.cta_group::2, M = 256, N = 256, K = 16 per instruction).
+//
+//   acc[m, n] = sum_k A[m, k] * W[n, k]            fp16 operands, fp32 accumulation in TMEM
+//
+// Why pairs: a single-CTA 128 x 256 tile needs 48 KB of operands per 512 tensor-core clocks (94 B/clk/SM); the L2
+// can deliver about 43 B/clk/SM with every SM streaming, so the main loop ran at ~45 % of the MMA rate.  In a pair
+// each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 weight rows); the MMA reads the
+// other half from the peer's shared memory.  32 KB per 512 clocks = 64 B/clk/SM — the same operand economy as the
+// 256 x 256 2-SM tiles cuBLAS uses on this part.
+//
+// Roles per CTA (192 threads), persistent over tiles:
+//   warp 0    TMA producer : both CTAs load their A rows and their half of B; completion bytes are credited to the
+//                            LEADER CTA's full barrier (cp.async.bulk.tensor ... cta_group::2)
+//   warp 1    MMA issuer   : leader CTA only; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs
+//   warps 2-9 epilogue     : each CTA drains its own 128 TMEM lanes x 256 columns (two warps per 32-lane
+//                            sub-partition, 128 columns each); double-buffered accumulators
+//                            (2 x 256 TMEM columns) let the epilogue of tile i overlap the main loop of tile i+1
+//
+// Epilogue I/O is coalesced: tcgen05.ld gives each lane one ROW (32 consecutive columns); the warp transposes the
+// 32 x 32 fp32 block through a padded shared-memory buffer so that, for global memory, 8 lanes cover 32 consecutive
+// columns of one row (128 B of fp32 / 64 B of fp16) — the residual read, the gated residual write and the fp16
+// activations all move as full sectors.  Only the transposed V copy is written lane-per-row (its fast axis is the
+// sequence position).
+#include "common.h"
+#include "gemm_params.cuh"
+#include "ptx.cuh"
+
+namespace lemas {
+
+constexpr int G2_BM = 128;   // rows per CTA (256 per pair)
+constexpr int G2_BN = 256;   // columns per pair tile
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 5;
+constexpr int G2_EPI_WARPS = 8;                        // two warps per TMEM sub-partition, each takes half the columns
+constexpr int G2_THREADS = 64 + 32 * G2_EPI_WARPS;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB: this CTA's half of the B tile
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_PITCH = 36;                           // floats per staged row (32 + 4: conflict-free float4 access)
+constexpr int G2_STG_BYTES = G2_EPI_WARPS * 32 * G2_PITCH * 4;
+constexpr int G2_OFF_STG = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_OFF_BAR = G2_OFF_STG + G2_STG_BYTES;
+constexpr int G2_SMEM = G2_OFF_BAR + 256 + 1024;
+
+DEVI uint2 pack4_half(float4 v) { return make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w)); }
+
+// One 32-row x 32-column block of the accumulator.  r[i] = acc[row_base + lane][col0 + i].
+// bias4 / gate4: this thread's 4 columns (col0 + 4*(lane&7) ..) of the per-column vectors, loaded by the caller at
+// tile start so their latency hides behind the main loop.  All global loads of the block are issued before any
+// dependent math or store — the compiler will not hoist them across the stores on its own.
+template <int EPI>
+DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], int row_base, int col0, int lane,
+                     float4 bias4, float4 gate4) {
+  const int M = p.rows;
+  if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
+    if (col0 >= 2 * p.inner) {  // V: transposed copy [b, head, d, pos]; lanes = consecutive positions
+      const int grow = row_base + lane;
+      float4 bv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (grow < M) {
+        const int b = grow / p.seq_len, pos = grow - b * p.seq_len;
+        const int vcol = col0 - 2 * p.inner;
+        const int heads = p.inner >> 6;
+        __half* dst = p.vt + ((long)(b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * p.vt_ld + pos;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[(long)(4 * j + 0) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 0]) + bv[j].x);
+          dst[(long)(4 * j + 1) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 1]) + bv[j].y);
+          dst[(long)(4 * j + 2) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 2]) + bv[j].z);
+          dst[(long)(4 * j + 3) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 3]) + bv[j].w);
+        }
+      }
+      return;
+    }
+  }
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int col = col0 + c4 * 4;
+
+  // ---- global loads of this block, issued up front
+  [[maybe_unused]] float4 pre[8];
+  if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row_base + it * 4 + rsub;
+      if (grow < M) pre[it] = *reinterpret_cast<const float4*>(p.resid + (long)grow * p.ldr + col);
+    }
+  } else if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
+    const int within = col % p.inner;
+    const bool rot = within < p.rope_cols;
+    const int pair0 = (within & 63) >> 1;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int grow = row_base + it * 4 + rsub;
+      pre[it] = make_float4(1.f, 0.f, 1.f, 0.f);
+      if (rot && grow < M)
+        pre[it] = __ldg(reinterpret_cast<const float4*>(p.rope + (long)(grow % p.seq_len) * 32 + pair0));
+    }
+  }
+
+  // ---- transpose through shared memory: lane-per-row -> 8 lanes per row
+  float4* srow = reinterpret_cast<float4*>(stg + lane * G2_PITCH);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + rsub;
+    const int grow = row_base + rr;
+    if (grow >= M) continue;
+    float4 v = *reinterpret_cast<const float4*>(stg + rr * G2_PITCH + c4 * 4);
+    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+    if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
+      const int b = grow / p.seq_len;
+      float4 g = gate4;
+      if (p.gate != nullptr && p.gate_bstride != 0)
+        g = __ldg(reinterpret_cast<const float4*>(p.gate + (long)b * p.gate_bstride + col));
+      const bool dead = p.row_valid != nullptr && (grow - b * p.seq_len) >= __ldg(p.row_valid + b);
+      float4 o = pre[it];
+      if (!dead) { o.x += g.x * v.x; o.y += g.y * v.y; o.z += g.z * v.z; o.w += g.w * v.w; }
+      *reinterpret_cast<float4*>(p.out32 + (long)grow * p.ld32 + col) = o;
+    } else if constexpr (EPI == LEMAS_EPI_BIAS_F16) {
+      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+    } else if constexpr (EPI == LEMAS_EPI_GELU_TANH_F16) {
+      v.x = gelu_tanh_f(v.x); v.y = gelu_tanh_f(v.y); v.z = gelu_tanh_f(v.z); v.w = gelu_tanh_f(v.w);
+      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+    } else if constexpr (EPI == LEMAS_EPI_GELU_ERF_F16) {
+      v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w);
+      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+    } else if constexpr (EPI == LEMAS_EPI_BIAS_F32) {
+      *reinterpret_cast<float4*>(p.out32 + (long)grow * p.ld32 + col) = v;
+    } else if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {  // q | k columns (V handled above); cs = (cos0, sin0, cos1, sin1)
+      const float4 cs = pre[it];
+      const float x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+      v.x = x0 * cs.x - x1 * cs.y; v.y = x1 * cs.x + x0 * cs.y;
+      v.z = x2 * cs.z - x3 * cs.w; v.w = x3 * cs.z + x2 * cs.w;
+      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+    }
+  }
+  __syncwarp();  // the staging buffer is rewritten by the next block
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+             const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_OFF_BAR);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* acc_full = empty_bar + G2_STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int m_tiles = (p.rows + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int n_tiles = p.n / G2_BN;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);    // leader's own arrive.expect_tx; both CTAs' TMA bytes are credited here
+      mbar_init(empty_bar + s, 1);   // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + a, 1);    // one multicast tcgen05.commit
+      mbar_init(acc_empty + a, 2 * G2_EPI_WARPS);   // every epilogue warp of both CTAs (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int n_idx = tile % n_tiles;
+        const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+        const int n0 = n_idx * G2_BN + (int)rank * (G2_BN / 2);
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);
+          const uint32_t full_leader = mapa_shared(smem_u32(full_bar + stage), 0);
+          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+          tma_load_2d_pair(sa, &tmA, full_leader, it * G2_BK, m0);
+          tma_load_2d_pair(sa + G2_A_BYTES, &tmW, full_leader, it * G2_BK, n0);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * G2_BM, G2_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait_cluster(acc_empty + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int it = 0; it < p.k_iters; ++it) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + G2_A_BYTES);
+#pragma unroll
+            for (int k = 0; k < G2_BK / 16; ++k)
+              umma_f16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_commit_pair(empty_bar + stage, 3);
+            if (it == p.k_iters - 1) umma_commit_pair(acc_full + acc, 3);
+          }
+          __syncwarp();
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int sub = warp & 3;           // TMEM sub-partition of this warp: lanes [32*sub, 32*sub+32)
+    const int half = (warp - 2) >> 2;   // which 128 columns of the 256-wide tile this warp drains
+    float* stg = reinterpret_cast<float*>(smem + G2_OFF_STG) + (warp - 2) * 32 * G2_PITCH;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int n_idx = tile % n_tiles;
+      const int row_base = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM + sub * 32;
+      const int n0 = n_idx * G2_BN;
+      // Per-column vectors (bias, gate) for this thread's 4 columns of each 32-column block are fetched one block
+      // ahead; block 0's are issued before the accumulator wait so their latency hides behind the main loop.
+      // The block loop stays rolled: these kernels run a few microseconds, every instruction executes only a
+      // handful of times, and a fully unrolled epilogue (~6 k instructions) was instruction-fetch bound.
+      const int ccol = n0 + (lane & 7) * 4;
+      auto load_bias = [&](int j) {
+        return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ccol + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto load_gate = [&](int j) {
+        if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32)
+          if (p.gate != nullptr && p.gate_bstride == 0) return __ldg(reinterpret_cast<const float4*>(p.gate + ccol + j * 32));
+        return make_float4(1.f, 1.f, 1.f, 1.f);
+      };
+      const int j0 = half * 4;
+      float4 bias_nxt = load_bias(j0), gate_nxt = load_gate(j0);
+      mbar_wait(acc_full + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + acc * G2_BN;
+      if (row_base < p.rows) {
+#pragma unroll 1
+        for (int j = j0; j < j0 + 4; ++j) {
+          const float4 bias4 = bias_nxt, gate4 = gate_nxt;
+          if (j < j0 + 3) { bias_nxt = load_bias(j + 1); gate_nxt = load_gate(j + 1); }
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + j * 32, r);
+          tmem_ld_wait();
+          epi2_block<EPI>(p, stg, r, row_base, n0 + j * 32, lane, bias4, gate4);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(acc_empty + acc), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still touch this CTA's memory / barriers
+  if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
+template <int EPI>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = gemm2_kernel<EPI>;
+  if (!configured) {
+    LEMAS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    configured = true;
+  }
+  const int tiles = ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
+  int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
+  if (pairs < 1) pairs = 1;
+  if (pairs > tiles) pairs = tiles;
+  kern<<<2 * pairs, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, p);
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
+bool gemm2_eligible(const lemas_gemm_desc& d) {
+  const bool epi_ok = d.epilogue == LEMAS_EPI_BIAS_F16 || d.epilogue == LEMAS_EPI_QKV_ROPE ||
+                      d.epilogue == LEMAS_EPI_GELU_TANH_F16 || d.epilogue == LEMAS_EPI_GELU_ERF_F16 ||
+                      d.epilogue == LEMAS_EPI_GATE_RESID_F32 || d.epilogue == LEMAS_EPI_BIAS_F32;
+  return epi_ok && d.batches == 1 && d.taps == 1 && d.group_cols == 0 && d.block_n == 256 && d.n % G2_BN == 0 &&
+         d.a_cols == d.k_per_tap && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
+}
+
+// Called by gemm_launch (gemm.cu) after validation, with the kernel parameters already filled in.
+int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p, cudaStream_t st) {
+  CUtensorMap tmA, tmW;
+  {
+    uint64_t dims[2] = {(uint64_t)d.a_cols, (uint64_t)d.rows};
+    uint64_t strides[1] = {(uint64_t)d.lda * 2};
+    uint32_t box[2] = {G2_BK, G2_BM};
+    LEMAS_TRY(make_tensor_map_f16(&tmA, d.a, 2, dims, strides, box));
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)d.ldw, (uint64_t)d.w_rows};
+    uint64_t strides[1] = {(uint64_t)d.ldw * 2};
+    uint32_t box[2] = {G2_BK, G2_BN / 2};
+    LEMAS_TRY(make_tensor_map_f16(&tmW, d.w, 2, dims, strides, box));
+  }
+  switch (d.epilogue) {
+    case LEMAS_EPI_BIAS_F16: return launch2<LEMAS_EPI_BIAS_F16>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_QKV_ROPE: return launch2<LEMAS_EPI_QKV_ROPE>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_GELU_TANH_F16: return launch2<LEMAS_EPI_GELU_TANH_F16>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_GELU_ERF_F16: return launch2<LEMAS_EPI_GELU_ERF_F16>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_GATE_RESID_F32: return launch2<LEMAS_EPI_GATE_RESID_F32>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_BIAS_F32: return launch2<LEMAS_EPI_BIAS_F32>(tmA, tmW, p, d.max_ctas, st);
+  }
+  return fail(LEMAS_ERR_INVALID, "gemm2: unsupported epilogue");
+}
+
+}  // namespace lemas

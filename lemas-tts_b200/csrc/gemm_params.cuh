@@ -1,0 +1,36 @@
+// Kernel-side parameters and activation helpers shared by the GEMM kernels (gemm.cu: single-CTA tiles with taps /
+// groups; gemm2.cu: CTA-pair 256x256 tiles).
+#pragma once
+#include "ptx.cuh"
+
+namespace lemas {
+
+struct GemmParams {
+  int batches, rows;      // A tiling: tiles never straddle a batch item
+  int n, k_iters, kc_per_tap, tap_pad, w_tap_stride, group_cols;
+  const float* bias;
+  __half* out16; int ld16;
+  float* out32; int ld32;
+  const float* resid; int ldr;
+  const float* gate; int gate_bstride;
+  const int* row_valid;
+  int seq_len;
+  const float2* rope; int rope_cols; int inner;
+  __half* vt; int vt_ld;
+};
+
+DEVI float gelu_tanh_f(float x) {
+  // 0.5 x (1 + tanh(u)) == x / (1 + exp(-2u)),  u = sqrt(2/pi) (x + 0.044715 x^3)
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));  // MUFU ex2 + rcp; exp overflow -> x/inf = 0, the correct limit
+}
+DEVI float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f)); }
+DEVI float mish_f(float x) {
+  // x * tanh(softplus(x)); tanh(log(1+e^x)) = (n^2 + 2n) / (n^2 + 2n + 2), n = e^x  (softplus threshold 20 as torch)
+  if (x > 20.0f) return x;
+  float n = __expf(x);
+  float a = n * (n + 2.0f);
+  return x * __fdividef(a, a + 2.0f);
+}
+
+}  // namespace lemas

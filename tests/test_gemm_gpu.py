@@ -204,3 +204,54 @@ def test_invalid_arguments_fail_loudly():
     w = torch.zeros(128, 100, device="cuda", dtype=torch.float16)
     with pytest.raises(RuntimeError):
         ops.gemm(a, w, epilogue=nv.EPI_BIAS_F16, out16=torch.zeros(128, 128, device="cuda", dtype=torch.float16))
+
+
+# ------------------------------------------------------------------ CTA-pair kernel (csrc/gemm2.cu, block_n=256, n % 256 == 0)
+
+
+@pytest.mark.parametrize("rows,k,n,max_ctas", [(4374, 1024, 1024, 0), (700, 2048, 1024, 0), (100, 64, 256, 0),
+                                               (300, 512, 512, 2), (1000, 1024, 768, 5), (257, 128, 256, 0)])
+def test_pair_gate_resid_and_bias_f32(rows, k, n, max_ctas):
+    from lemas_tts import ops, _native as nv
+
+    B = 2 if rows % 2 == 0 else 1
+    N = rows // B
+    a = _rand((rows, k), 40, dtype=torch.float16)
+    w = _rand((n, k), 41, 1 / math.sqrt(k), torch.float16)
+    bias, gate, x = _rand((n,), 42), _rand((B, n), 43), _rand((rows, n), 44)
+    valid = torch.tensor([N, max(1, N // 3)][:B], device="cuda", dtype=torch.int32)
+    pre = a.float() @ w.float().T + bias
+    keep = (torch.arange(N, device="cuda")[None] < valid[:, None]).reshape(-1, 1)
+    ref = x + gate.repeat_interleave(N, 0) * torch.where(keep, pre, torch.zeros_like(pre))
+    out = x.clone()
+    ops.gemm(a, w, epilogue=nv.EPI_GATE_RESID_F32, bias=bias, block_n=256, out32=out, resid=out, gate=gate,
+             gate_bstride=n, row_valid=valid, seq_len=N, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    _close(out, ref, what="pair gate_resid")
+    out2 = torch.full((rows, n), 3.0, device="cuda")
+    ops.gemm(a, w, epilogue=nv.EPI_BIAS_F32, bias=bias, block_n=256, out32=out2, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    _close(out2, pre, what="pair bias_f32")
+    # shared gate row (gate_bstride == 0), no row mask: the sampler's FF2 call
+    out3 = x.clone()
+    ops.gemm(a, w, epilogue=nv.EPI_GATE_RESID_F32, bias=bias, block_n=256, out32=out3, resid=out3, gate=gate[0],
+             seq_len=N, max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    _close(out3, x + gate[0] * pre, what="pair gate_resid shared gate")
+
+
+def test_pair_matches_single_cta_kernel_bitwise_inputs():
+    """Same operands through both kernels (block_n 128 -> gemm.cu, 256 -> gemm2.cu): results agree to fp32 rounding."""
+    from lemas_tts import ops, _native as nv
+
+    rows, k, n = 1500, 1024, 2048
+    a = _rand((rows, k), 50, dtype=torch.float16)
+    w = _rand((n, k), 51, 1 / math.sqrt(k), torch.float16)
+    bias = _rand((n,), 52)
+    o1 = torch.zeros(rows, n, device="cuda", dtype=torch.float16)
+    o2 = torch.zeros_like(o1)
+    ops.gemm(a, w, epilogue=nv.EPI_GELU_TANH_F16, bias=bias, block_n=128, out16=o1)
+    ops.gemm(a, w, epilogue=nv.EPI_GELU_TANH_F16, bias=bias, block_n=256, out16=o2)
+    torch.cuda.synchronize()
+    assert (o1.float() - o2.float()).abs().max() <= 2e-3
+    _close(o2, F.gelu(a.float() @ w.float().T + bias, approximate="tanh"), what="pair gelu")

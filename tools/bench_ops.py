@@ -27,13 +27,22 @@ def r32(*s):
 
 
 def timeit(fn, flops=None, bytes_=None, name="", iters=20):
+    """`iters` back-to-back launches captured in a CUDA graph (no host launch overhead in the number)."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / iters * 1e3
@@ -78,9 +87,13 @@ for bn in (128, 256):
     timeit(lambda: ops.gemm(a_d, w_qkv, epilogue=nv.EPI_QKV_ROPE, bias=b_qkv, block_n=bn, out16=qk, rope=rope,
                             rope_cols=D, inner=D, vt=vt, seq_len=seq), 2.0 * M * D * 3 * D,
            name=f"gemm K1024 N3072 qkv_rope bn{bn}  (qkv)")
-timeit(lambda: ops.attention(qk, vt, B2, seq, H), 4.0 * seq * seq * D * B2, name="attention")
+att_out = torch.empty(M, D, device=dev, dtype=torch.float16)
+timeit(lambda: nv.check(nv.load().lemas_attention_f16(nv.ptr(qk), 2 * D, nv.ptr(vt), npad, None, nv.ptr(att_out), B2, seq,
+                                                       H, nv.stream())), 4.0 * seq * seq * D * B2, name="attention")
 sc, sh = r32(D), r32(D)
-timeit(lambda: ops.ln_modulate(x, sc, sh, seq_len=seq), bytes_=6.0 * M * D, name="ln_modulate")
+ln_out = torch.empty(M, D, device=dev, dtype=torch.float16)
+timeit(lambda: nv.check(nv.load().lemas_ln_modulate(nv.ptr(x), nv.ptr(sc), nv.ptr(sh), 0, nv.ptr(ln_out), M, D, seq,
+                                                     nv.stream())), bytes_=6.0 * M * D, name="ln_modulate")
 # cuBLAS reference points (library, for context only)
 wt = w_ff1.t().contiguous()
 timeit(lambda: torch.matmul(a_d, wt), 2.0 * M * D * F, name="torch.matmul fp16 K1024 N2048 (cuBLAS)")
