@@ -2,24 +2,39 @@
 //
 //   O = softmax(Q K^T / 8 + keymask) V        modules.py:483-491 (F.scaled_dot_product_attention call site)
 //
-// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM so that one CTA's softmax
-// overlaps the other's MMAs.  Roles (192 threads):
+// What bounds this kernel on B200: with head_dim 64 a 128 x 128 score block costs 512 tensor-core clocks (QK^T + PV)
+// but 16 384 exponentials, and the SFU delivers 16 exp2 / clk / SM (measured, profiles/r01b_mufu_exp2_throughput.log;
+// the packed f16x2 / bf16x2 forms are split into two MUFU ops and gain nothing) = 1024 clocks.  The design goal is
+// therefore to keep the SFU saturated: many independent softmax warps, no per-block work besides max / exp / sum / pack.
+//
+// One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM.  Roles (320 threads):
 //   warp 0    TMA producer : Q tile once, then K tile [128 keys x 64] and V^T tile [64 x 128 keys] per KV block
-//                            into a 2-stage ring (128B swizzle, mbarrier tx-count)
-//   warp 1    MMA issuer   : S = Q K^T (M128 N128 K16 x4) into TMEM cols [0,128); O_part = P V (M128 N64 K16 x8)
-//                            into TMEM cols [128,192); S for block j+1 is issued while softmax j runs
-//   warps 2-5 softmax      : thread == query row (tcgen05.ld 32x32b gives each lane one row): two passes over S in
-//                            TMEM (row max, then exp2 / row sum), P written as fp16 into the swizzled K-major smem
-//                            layout UMMA reads as the A operand; O accumulated in registers with online rescale.
-// Fully masked KV blocks (keys >= kv_len) are skipped; the partial block is masked to -inf.
+//                            into two 2-slot rings (128B swizzle, mbarrier tx-count); K slots recycle after S = Q K^T,
+//                            V slots after P V, so K runs a block further ahead
+//   warp 1    MMA issuer   : S = Q K^T (M128 N128 K16 x4) into TMEM cols [0,128); S for block j+1 is issued while the
+//                            softmax of block j runs.  P V is issued as TWO independent streams, one per 64-key half
+//                            of the block: O_A += P[:, 0:64] V[0:64], O_B += P[:, 64:128] V[64:128] (M128 N64 K16 x4
+//                            each), accumulated IN TMEM across all KV blocks (cols [128,192) and [192,256)).
+//   warps 2-9 softmax      : warps 2-5 own key half A, warps 6-9 key half B; thread == query row (tcgen05.ld 32x32b
+//                            gives each lane one row).  Each half runs its own online softmax (own running max and
+//                            row sum) over its 64 keys of every block — intra-CTA split-KV — so the two warps that
+//                            share a row never synchronise inside the loop; the halves are merged once at the end:
+//                            O = (w_A O_A + w_B O_B) / (w_A l_A + w_B l_B),  w_X = 2^((m_X - max(m_A, m_B)) c).
+//                            The accumulators are rescaled lazily: O_X and l_X keep the scale of a reference max that
+//                            is only advanced when a block's max exceeds it by more than 2^8 (P then stays <= 256,
+//                            exact in fp16 terms); after the first blocks this almost never fires, so the steady
+//                            state per block is: one TMEM read of S, max, exp2, sum, fp16 pack, swizzled smem store.
+// Fully masked KV blocks (keys >= kv_len) are skipped; the partial block is masked to zero probability.
 // K comes from the fused QKV buffer [b*seq, ld_qk]; V is read from the transposed copy [b, head, 64, vt_ld] that
 // the QKV GEMM epilogue writes, so both MMAs use K-major operands.
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
 namespace lemas {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BN = 128;   // keys per KV block
 constexpr int ATT_D = 64;
@@ -32,15 +47,25 @@ constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;         // 32 KB (two 16 KB hal
 constexpr int ATT_KV_STAGE = ATT_K_BYTES + ATT_V_BYTES;
 constexpr int ATT_OFF_KV = ATT_Q_BYTES;
 constexpr int ATT_OFF_P = ATT_OFF_KV + ATT_STAGES * ATT_KV_STAGE;
+constexpr int ATT_OFF_XCH = ATT_OFF_P;                   // float2 [2 halves][128 rows] (reference max, row sum):
+                                                         // reuses the P buffer after the last P V has retired
 constexpr int ATT_OFF_BAR = ATT_OFF_P + ATT_P_BYTES;
-constexpr int ATT_SMEM = ATT_OFF_BAR + 128;
+constexpr int ATT_SMEM = ATT_OFF_BAR + 128;              // 112.1 KB: two CTAs per SM
+
+constexpr float ATT_RESCALE_LOG2 = 8.0f;  // advance the reference max only past 2^8 growth
 
 struct AttnParams {
+  long long* trace;   // debug: clock64 stamps of CTA (1,0,0) [warp][block][8]; nullptr in production
   const int* kv_len;
   __half* out;
   int seq, heads, inner;
 };
 
+DEVI float fmax3f(float a, float b, float c) {  // 3-input max: one FMNMX3 on sm_100
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
 DEVI float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -53,13 +78,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                 // [2]
-  uint64_t* kv_empty = bars + 3;                // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* o_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;                  // [2]  K and V^T travel through separate 2-slot rings: a K slot is
+  uint64_t* k_empty = bars + 3;                 // [2]  free as soon as S_j = Q K_j^T has retired, a V slot only after
+  uint64_t* v_full = bars + 5;                  // [2]  P V_j — so K_{j+2} streams in a whole block earlier than a
+  uint64_t* v_empty = bars + 7;                 // [2]  shared ring would allow and S_{j+1} is never late
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_empty = bars + 10;
+  uint64_t* p_full = bars + 11;                 // [2] per key half
+  uint64_t* o_full = bars + 13;                 // [2] per key half
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -81,13 +108,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     tma_prefetch_desc(&tmVT);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_STAGES; ++s) {
-      mbar_init(kv_full + s, 1);
-      mbar_init(kv_empty + s, 1);
+      mbar_init(k_full + s, 1);
+      mbar_init(k_empty + s, 1);
+      mbar_init(v_full + s, 1);
+      mbar_init(v_empty + s, 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(s_empty, 8);            // one arrival per softmax warp
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(p_full + x, 4);         // one arrival per softmax warp of the half
+      mbar_init(o_full + x, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -96,7 +127,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + ATT_BN;
+  const uint32_t tmem_o = tmem_base + ATT_BN;   // + 64 * half
 
   if (warp == 0) {
     if (elect_one()) {
@@ -104,12 +135,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       tma_load_3d(smem, &tmQK, q_full, h * ATT_D, q0, b);
       for (int j = 0; j < n_blocks; ++j) {
         const int s = j & 1;
-        mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, ATT_KV_STAGE);
+        const uint32_t ph = ((j >> 1) & 1) ^ 1;
         uint8_t* sk = smem + ATT_OFF_KV + s * ATT_KV_STAGE;
-        tma_load_3d(sk, &tmQK, kv_full + s, p.inner + h * ATT_D, j * ATT_BN, b);
-        tma_load_3d(sk + ATT_K_BYTES, &tmVT, kv_full + s, j * ATT_BN, 0, b * p.heads + h);
-        tma_load_3d(sk + ATT_K_BYTES + ATT_V_BYTES / 2, &tmVT, kv_full + s, j * ATT_BN + 64, 0, b * p.heads + h);
+        mbar_wait(k_empty + s, ph);
+        mbar_arrive_expect_tx(k_full + s, ATT_K_BYTES);
+        tma_load_3d(sk, &tmQK, k_full + s, p.inner + h * ATT_D, j * ATT_BN, b);
+        mbar_wait(v_empty + s, ph);
+        mbar_arrive_expect_tx(v_full + s, ATT_V_BYTES);
+        tma_load_3d(sk + ATT_K_BYTES, &tmVT, v_full + s, j * ATT_BN, 0, b * p.heads + h);
+        tma_load_3d(sk + ATT_K_BYTES + ATT_V_BYTES / 2, &tmVT, v_full + s, j * ATT_BN + 64, 0, b * p.heads + h);
       }
     }
   } else if (warp == 1) {
@@ -123,139 +157,169 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 #pragma unroll
       for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
       umma_commit(s_full);
+      umma_commit(k_empty + (j & 1));
     };
     mbar_wait(q_full, 0);
-    mbar_wait(kv_full + 0, 0);
+    mbar_wait(k_full + 0, 0);
     tc_fence_after();
     if (elect_one()) issue_s(0);
     __syncwarp();
     for (int j = 0; j < n_blocks; ++j) {
       if (j + 1 < n_blocks) {
-        mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
-        mbar_wait(s_empty, j & 1);  // softmax has pulled S_j out of TMEM
+        mbar_wait(k_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+        mbar_wait(s_empty, j & 1);  // every softmax thread has pulled its part of S_j out of TMEM
         tc_fence_after();
         if (elect_one()) issue_s(j + 1);
         __syncwarp();
       }
-      mbar_wait(p_full, j & 1);  // P_j is in smem (and O_part_{j-1} has been consumed)
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sv = smem_u32(smem + ATT_OFF_KV + (j & 1) * ATT_KV_STAGE + ATT_K_BYTES);
+      const uint32_t sv = smem_u32(smem + ATT_OFF_KV + (j & 1) * ATT_KV_STAGE + ATT_K_BYTES);
+      mbar_wait(v_full + (j & 1), (j >> 1) & 1);
 #pragma unroll
-        for (int ks = 0; ks < ATT_BN / 16; ++ks) {
-          const uint64_t adesc = umma_desc_sw128(sp + (ks >> 2) * (ATT_P_BYTES / 2)) + 2 * (ks & 3);
-          const uint64_t bdesc = umma_desc_sw128(sv + (ks >> 2) * (ATT_V_BYTES / 2)) + 2 * (ks & 3);
-          umma_f16_ss(tmem_o, adesc, bdesc, idesc_o, ks != 0);
+      for (int x = 0; x < 2; ++x) {  // O_x (+)= P_j[:, 64x : 64x+64] V_j[64x : 64x+64]
+        mbar_wait(p_full + x, j & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = umma_desc_sw128(sp + x * (ATT_P_BYTES / 2));
+          const uint64_t bdesc = umma_desc_sw128(sv + x * (ATT_V_BYTES / 2));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_o + x * ATT_D, adesc + 2 * ks, bdesc + 2 * ks, idesc_o, (j | ks) != 0 ? 1u : 0u);
+          umma_commit(o_full + x);
+          if (x == 1) umma_commit(v_empty + (j & 1));
         }
-        umma_commit(o_full);
-        umma_commit(kv_empty + (j & 1));
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    const int sub = warp & 3;
-    const int r = sub * 32 + lane;  // query row inside the tile == TMEM lane
+    const int sub = warp & 3;          // TMEM sub-partition: lanes [32*sub, 32*sub+32)
+    const int half = (warp - 2) >> 2;  // key half of every KV block this warp owns
+    const int r = sub * 32 + lane;     // query row inside the tile == TMEM lane
     const uint32_t lane_addr = uint32_t(sub * 32) << 16;
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float o[ATT_D];
-#pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
-    uint8_t* prow = smem + ATT_OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+    float m_ref = -INFINITY;           // max the accumulators O_half / l are currently scaled by
+    float l_run = 0.f;
+    uint8_t* prow = smem + ATT_OFF_P + half * (ATT_P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t t_s = tmem_s + lane_addr + half * 64;
+    const uint32_t t_o = tmem_o + lane_addr + half * ATT_D;
 
     for (int j = 0; j < n_blocks; ++j) {
-      const int valid = kvl - j * ATT_BN;  // keys of this block that exist (>= 1)
+      const int valid = min(max(kvl - j * ATT_BN - half * 64, 0), 64);  // keys of this half-block that exist
+      const bool tr = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 32;
+      long long* tp = p.trace + ((warp - 2) * 32 + j) * 8;
+      if (tr) tp[0] = clock64();
       mbar_wait(s_full, j & 1);
+      if (tr) tp[1] = clock64();
       tc_fence_after();
-      // pass 1: row max
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(t_s, s0);
+      tmem_ld_32x32(t_s + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(s_empty);  // S_j is in registers (tcgen05.wait::ld is warp-wide): S_{j+1} may land
+      if (tr) tp[2] = clock64();
+
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_BN; cc += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_addr + cc, v);
-        tmem_ld_wait();
-        if (cc + 32 <= valid) {
+      if (valid == 64) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains, not one of 32
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2f((m_run - m_new) * c);
-      const float mc = m_new * c;
-      m_run = m_new;
-      // fold in the previous block's P V (also guarantees the P buffer is free again)
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_o + lane_addr + hh * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[hh * 32 + i] = o[hh * 32 + i] * alpha_pending + __uint_as_float(v[i]);
-        }
-      }
-      alpha_pending = alpha;
-      // pass 2: p = exp2(s*c - m*c), row sum, fp16 P into swizzled smem
-      float rs = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < ATT_BN; cc += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_s + lane_addr + cc, v);
-        tmem_ld_wait();
-        float pv[32];
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], __uint_as_float(s0[i]), __uint_as_float(s1[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = ex2f(fmaf(__uint_as_float(v[i]), c, -mc));
-          if (cc + 32 > valid && cc + i >= valid) e = 0.f;
-          pv[i] = e;
-          rs += e;
-        }
-        uint8_t* dst = prow + (cc >> 6) * (ATT_P_BYTES / 2);
-        const int u0 = (cc & 32) >> 3;  // first 16-byte unit of this chunk inside the 128-byte row
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 w;
-          w.x = pack_half2(pv[8 * u + 0], pv[8 * u + 1]);
-          w.y = pack_half2(pv[8 * u + 2], pv[8 * u + 3]);
-          w.z = pack_half2(pv[8 * u + 4], pv[8 * u + 5]);
-          w.w = pack_half2(pv[8 * u + 6], pv[8 * u + 7]);
-          *reinterpret_cast<uint4*>(dst + (((u0 + u) ^ (r & 7)) << 4)) = w;
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(s0[i]));
+          if (i + 32 < valid) mx = fmaxf(mx, __uint_as_float(s1[i]));
         }
       }
-      l_run = l_run * alpha + rs;
-      tc_fence_before();
-      mbar_arrive(s_empty);        // S_j fully read: the MMA warp may overwrite it with S_{j+1}
-      fence_proxy_async_smem();    // make the generic-proxy P stores visible to the tensor core (async proxy)
-      mbar_arrive(p_full);
+      // lazy rescale: advance the reference max only when this block exceeds it by more than 2^8 (warp-uniform
+      // decision, tcgen05.ld/st are warp-collective)
+      const bool grow = (mx - m_ref) * c > ATT_RESCALE_LOG2;  // also true for the first finite max (m_ref = -inf)
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_ref;
+        const float alpha = (m_ref == -INFINITY) ? 0.f : ex2f((m_ref - m_new) * c);
+        l_run *= alpha;
+        if (j > 0) {  // O_half holds the sum of blocks < j: rescale it in TMEM once P V_{j-1} has retired
+          mbar_wait(o_full + half, (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < ATT_D; cc += 8) {  // narrow chunks: S_j (64 registers) stays live across this
+            uint32_t v[8];
+            tmem_ld_32x32_x8(t_o + cc, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32_x8(t_o + cc, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        m_ref = m_new;
+      }
+      const float mc = (m_ref == -INFINITY) ? 0.f : m_ref * c;
+      if (tr) tp[3] = clock64();
+
+      // exp2 of the whole half-row into packed fp16 registers first; only then wait for the P buffer (free once
+      // P V_{j-1} has read it) — waiting before the exponentials re-synchronised the four warps of a half every block
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+      auto exp_block = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;  // full half-block: no per-element masking code at all
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = 2 * i;
+          float e0 = ex2f(fmaf(__uint_as_float(col < 32 ? s0[col & 31] : s1[col & 31]), c, -mc));
+          float e1 = ex2f(fmaf(__uint_as_float(col + 1 < 32 ? s0[(col + 1) & 31] : s1[(col + 1) & 31]), c, -mc));
+          if (!kFull && col >= valid) e0 = 0.f;
+          if (!kFull && col + 1 >= valid) e1 = 0.f;
+          rs4[i & 3] += e0 + e1;
+          pk[i] = pack_half2(e0, e1);
+        }
+      };
+      if (valid == 64) exp_block(std::true_type{}); else exp_block(std::false_type{});
+      if (tr) tp[4] = clock64();
+      if (j > 0) mbar_wait(o_full + half, (j - 1) & 1);
+      if (tr) tp[5] = clock64();
+#pragma unroll
+      for (int u = 0; u < 8; ++u)  // 16-byte units of the 128-byte (64 keys x fp16) swizzled row
+        *reinterpret_cast<uint4*>(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+      fence_proxy_async_smem();  // make the generic-proxy P stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full + half);
+      if (tr) tp[6] = clock64();
     }
-    // last block's P V
-    mbar_wait(o_full, (n_blocks - 1) & 1);
+
+    // ---- merge the two key halves and normalise
+    mbar_wait(o_full + 0, (n_blocks - 1) & 1);
+    mbar_wait(o_full + 1, (n_blocks - 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_o + lane_addr + hh * 32, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[hh * 32 + i] = o[hh * 32 + i] * alpha_pending + __uint_as_float(v[i]);
-    }
+    float2* xch = reinterpret_cast<float2*>(smem + ATT_OFF_XCH);  // P buffer: free now that every P V has retired
+    xch[half * ATT_BM + r] = make_float2(m_ref, l_run);
+    named_bar_sync(1 + sub, 64);  // the two warps that share these 32 rows
+    const float2 other = xch[(half ^ 1) * ATT_BM + r];
+    const float m_all = fmaxf(m_ref, other.x);
+    const float w_me = (m_ref == -INFINITY) ? 0.f : ex2f((m_ref - m_all) * c);
+    const float w_ot = (other.x == -INFINITY) ? 0.f : ex2f((other.x - m_all) * c);
+    const float inv = 1.0f / (w_me * l_run + w_ot * other.y);
+    const float wa = (half == 0 ? w_me : w_ot) * inv, wb = (half == 0 ? w_ot : w_me) * inv;
+    uint32_t oa[32], ob[32];  // this warp outputs head-dim columns [32*half, 32*half+32)
+    tmem_ld_32x32(tmem_o + lane_addr + half * 32, oa);
+    tmem_ld_32x32(tmem_o + lane_addr + ATT_D + half * 32, ob);
+    tmem_ld_wait();
     const int row = q0 + r;
     if (row < p.seq) {
-      const float inv = 1.0f / l_run;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long)b * p.seq + row) * p.inner + h * ATT_D);
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((long)b * p.seq + row) * p.inner + h * ATT_D + half * 32);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = __uint_as_float(oa[8 * u + i]) * wa + __uint_as_float(ob[8 * u + i]) * wb;
         uint4 w;
-        w.x = pack_half2(o[8 * u + 0] * inv, o[8 * u + 1] * inv);
-        w.y = pack_half2(o[8 * u + 2] * inv, o[8 * u + 3] * inv);
-        w.z = pack_half2(o[8 * u + 4] * inv, o[8 * u + 5] * inv);
-        w.w = pack_half2(o[8 * u + 6] * inv, o[8 * u + 7] * inv);
+        w.x = pack_half2(o[0], o[1]);
+        w.y = pack_half2(o[2], o[3]);
+        w.z = pack_half2(o[4], o[5]);
+        w.w = pack_half2(o[6], o[7]);
         dst[u] = w;
       }
     }
@@ -269,6 +333,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 }  // namespace lemas
 
 using namespace lemas;
+
+static long long* g_att_trace = nullptr;
+// debug aid (not part of the public header): device buffer of 8 warps x 32 blocks x 8 int64 clock stamps
+extern "C" void lemas_debug_attention_trace(void* buf) { g_att_trace = static_cast<long long*>(buf); }
 
 extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                                    void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
@@ -295,6 +363,7 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
     configured = true;
   }
   AttnParams p;
+  p.trace = g_att_trace;
   p.kv_len = kv_len;
   p.out = static_cast<__half*>(out16);
   p.seq = seq;

@@ -88,6 +88,8 @@ for bn in (128, 256):
                             rope_cols=D, inner=D, vt=vt, seq_len=seq), 2.0 * M * D * 3 * D,
            name=f"gemm K1024 N3072 qkv_rope bn{bn}  (qkv)")
 att_out = torch.empty(M, D, device=dev, dtype=torch.float16)
+qk = torch.randn(M, 2 * D, device=dev, generator=g).half()  # unit-variance q, k: scores/8 ~ N(0, 1) like LN'd activations
+vt = torch.randn(B2, H, 64, npad, device=dev, generator=g).half()
 timeit(lambda: nv.check(nv.load().lemas_attention_f16(nv.ptr(qk), 2 * D, nv.ptr(vt), npad, None, nv.ptr(att_out), B2, seq,
                                                        H, nv.stream())), 4.0 * seq * seq * D * B2, name="attention")
 sc, sh = r32(D), r32(D)
