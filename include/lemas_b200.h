@@ -186,7 +186,9 @@ typedef struct lemas_sample_args {
   const float* rope;          /* fp32 [seq, 32, 2] cos/sin table                                                */
   float* trajectory;          /* optional fp32 [steps+1, batch, seq, mel] (cfm.py:456), NULL to skip            */
   void* workspace; int64_t workspace_bytes;
-  int32_t use_graph;          /* 1: capture one ODE step into a CUDA graph and replay it                        */
+  int32_t use_graph;          /* 1: capture ONE ODE step into a CUDA graph (cached per shape/workspace in the engine)
+                                 and replay it for every step; step-dependent values are read from device memory.
+                                 Ignored (eager launches) when a trajectory is requested or profiling is on.      */
 } lemas_sample_args;
 
 /* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */

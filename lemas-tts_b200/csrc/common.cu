@@ -15,6 +15,7 @@ int fail(int code, const std::string& msg) {
 
 static std::atomic<int64_t> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launches_so_far() { return g_launches.load(); }
 
 int sm_count() {
   static int n = 0;

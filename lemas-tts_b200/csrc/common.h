@@ -14,6 +14,7 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 int sm_count();
 void count_launches(int n);
+int64_t launches_so_far();
 
 #define LEMAS_CUDA_OK(expr)                                                                          \
   do {                                                                                               \

@@ -189,6 +189,69 @@ __global__ void cfg_euler_kernel(const float* __restrict__ pred, int ld_pred, fl
   for (int k = 0; k < copies; ++k) x16[((long)k * rows + row) * ld_x16 + c] = h;
 }
 
+// Same update with the step's scalars read from device memory (graph-replayed ODE steps: the launch arguments of a
+// captured step are frozen, so everything that changes from step to step lives in `state`).
+//   state[0] = cfg * (1 - t)^2, state[1] = dt, state[2] = bit pattern of the step index
+__global__ void cfg_euler_dev_kernel(const float* __restrict__ pred, int ld_pred, float* __restrict__ y,
+                                     __half* __restrict__ x16, int ld_x16, int copies, float* __restrict__ traj,
+                                     long traj_stride, int rows, int mel, const float* __restrict__ state, int use_cfg) {
+  const long total = (long)rows * mel;
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float cfg_t = state[0], dt = state[1];
+  const int step = __float_as_int(state[2]);
+  const long row = i / mel;
+  const int c = (int)(i - row * mel);
+  float f = pred[row * ld_pred + c];
+  if (use_cfg) {
+    const float pu = pred[(rows + row) * ld_pred + c];
+    f = f + (f - pu) * cfg_t;
+    f = fminf(fmaxf(f, -20.f), 20.f);
+  }
+  const float yn = y[i] + dt * f;
+  y[i] = yn;
+  if (traj) traj[(long)(step + 1) * traj_stride + i] = yn;
+  const __half h = __float2half_rn(yn);
+  for (int k = 0; k < copies; ++k) x16[((long)k * rows + row) * ld_x16 + c] = h;
+}
+
+// Start of an ODE step (single block): copy this step's row of the pre-computed AdaLN modulation table into the
+// fixed buffer every kernel of the step reads, publish the step scalars, advance the step counter.
+__global__ void __launch_bounds__(1024)
+step_begin_kernel(const float* __restrict__ mod_table, long mod_w, float* __restrict__ mod_cur,
+                  const float* __restrict__ t_grid, int* __restrict__ step_ctr, float* __restrict__ state,
+                  float cfg_strength) {
+  const int step = *step_ctr;
+  __syncthreads();  // everyone has read the counter before thread 0 advances it
+  const float4* src = reinterpret_cast<const float4*>(mod_table + (long)step * mod_w);
+  float4* dst = reinterpret_cast<float4*>(mod_cur);
+  for (long i = threadIdx.x; i < mod_w / 4; i += blockDim.x) dst[i] = src[i];
+  if (threadIdx.x == 0) {
+    const float t = t_grid[step];
+    const float one_minus_t = 1.0f - t;
+    state[0] = cfg_strength * (one_minus_t * one_minus_t);  // cfm.py:420
+    state[1] = t_grid[step + 1] - t;
+    state[2] = __int_as_float(step);
+    *step_ctr = step + 1;
+  }
+}
+
+int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const float* t_grid, int* step_ctr,
+                      float* state, float cfg_strength, cudaStream_t st) {
+  step_begin_kernel<<<1, 1024, 0, st>>>(mod_table, mod_w, mod_cur, t_grid, step_ctr, state, cfg_strength);
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
+int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
+                         long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st) {
+  const long total = (long)rows * mel;
+  cfg_euler_dev_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(pred, ld_pred, y, (__half*)x16, ld_x16, copies, traj,
+                                                                  traj_stride, rows, mel, state, use_cfg);
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Vocos ConvNeXtBlock front: depthwise conv k=7 pad 3 over time, then LayerNorm(affine) -> fp16.
 // One warp per (b, t) row; weights tap-major [7, dim].

@@ -9,6 +9,10 @@
 namespace lemas {
 
 int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream);
+int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const float* t_grid, int* step_ctr,
+                      float* state, float cfg_strength, cudaStream_t st);
+int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
+                         long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st);
 
 struct Carver {
   uint8_t* base;
@@ -25,8 +29,8 @@ struct Carver {
 
 struct DitBuffers {
   __half *x16, *ct16, *h0_16, *c1_16, *a16, *o16, *qk16, *vt16, *ff16;
-  float *inv_embed, *h0, *x, *pred, *t_dev, *sinus, *t1, *temb, *mod;
-  int* kv_len2;
+  float *inv_embed, *h0, *x, *pred, *t_dev, *sinus, *t1, *temb, *mod, *mod_cur, *state, *y_state;
+  int *kv_len2, *step_ctr;
   int npad;
   int64_t bytes;
 };
@@ -56,6 +60,10 @@ static DitBuffers carve(const lemas_dit_config& c, int batch, int seq, int steps
   b.temb = cv.take<float>((int64_t)steps * D);
   b.mod = cv.take<float>((int64_t)steps * ((int64_t)c.depth * 6 * D + 2 * D));
   b.kv_len2 = cv.take<int>(2 * batch);
+  b.mod_cur = cv.take<float>((int64_t)c.depth * 6 * D + 2 * D);
+  b.state = cv.take<float>(4);
+  b.step_ctr = cv.take<int>(1);
+  b.y_state = cv.take<float>((int64_t)batch * seq * c.mel_dim);
   b.bytes = align_up(cv.off, 1024);
   return b;
 }
@@ -73,6 +81,18 @@ struct lemas_engine {
   bool profile = false;
   std::vector<ProfRecord> records;     // event pairs in flight since the last profile_read
   std::vector<cudaEvent_t> free_events;
+  // One captured ODE step per (shape, workspace) — replayed `steps` times; everything step-dependent is read from
+  // device memory (step_begin_kernel), so the same executable graph serves every step and every later call.
+  struct StepGraph {
+    int batch, seq, variants, has_kv, has_traj;
+    float cfg;
+    const void *ws, *rope, *traj;
+    cudaGraphExec_t exec;
+    int nodes;
+  };
+  std::vector<StepGraph> graphs;
+  cudaStream_t cap_stream = nullptr;   // capture happens on a private stream: the caller's may be the legacy default
+                                       // stream, which cannot be captured; replays go to the caller's stream
 };
 
 // Brackets one launch with events when profiling is on (lemas_engine_profile); otherwise free.
@@ -122,6 +142,8 @@ void lemas_engine_destroy(lemas_engine* e) {
   if (!e) return;
   for (auto& r : e->records) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto ev : e->free_events) cudaEventDestroy(ev);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
 }
 
@@ -281,6 +303,25 @@ static int check_args(const lemas_engine* e, const lemas_sample_args* a, int ste
 
 extern "C" {
 
+// One ODE step with every step-dependent quantity read from device memory: modulation row -> mod_cur, (cfg_t, dt,
+// step) -> state.  Identical launch arguments for every step, so it can be captured once and replayed.
+static int ode_step(lemas_engine* e, const DitBuffers& b, const lemas_sample_args* a, int variants, const int* kv2,
+                    float* y, cudaStream_t st) {
+  const lemas_dit_config& c = e->cfg;
+  const int rows = a->batch * a->seq;
+  const int64_t mod_w = (int64_t)c.depth * 6 * c.dim + 2 * c.dim;
+  {
+    PROF(LEMAS_PROF_CFG_EULER);
+    LEMAS_TRY(step_begin_launch(b.mod, mod_w, b.mod_cur, b.t_dev, b.step_ctr, b.state,
+                                variants == 2 ? a->cfg_strength : 0.f, st));
+  }
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, st));
+  PROF(LEMAS_PROF_CFG_EULER);
+  LEMAS_TRY(cfg_euler_dev_launch(b.pred, 128, y, b.x16, 128, variants, a->trajectory, (long)rows * c.mel_dim, rows,
+                                 c.mel_dim, b.state, variants == 2 ? 1 : 0, st));
+  return LEMAS_OK;
+}
+
 int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DitBuffers b;
@@ -290,21 +331,60 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   LEMAS_REQUIRE(variants == 1 || a->text_uncond, "lemas_sampler_run: text_uncond required when cfg_strength > 0");
   const lemas_dit_config& c = e->cfg;
   const int rows = a->batch * a->seq;
-  const int64_t mod_w = (int64_t)c.depth * 6 * c.dim + 2 * c.dim;
   LEMAS_TRY(prepare(e, b, a, variants, a->steps, a->t_grid_host, st));
+  // prepare() uploaded t[0..steps-1]; the step kernels also need t[steps] for the last dt
+  LEMAS_CUDA_OK(cudaMemcpyAsync(b.t_dev + a->steps, a->t_grid_host + a->steps, sizeof(float), cudaMemcpyHostToDevice, st));
+  LEMAS_CUDA_OK(cudaMemsetAsync(b.step_ctr, 0, sizeof(int), st));
   const int64_t state = (int64_t)rows * c.mel_dim;
   if (a->trajectory)
     LEMAS_CUDA_OK(cudaMemcpyAsync(a->trajectory, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
   const int* kv2 = a->kv_len ? b.kv_len2 : nullptr;
-  for (int i = 0; i < a->steps; ++i) {
-    LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod + i * mod_w, kv2, a->rope, b.pred, st));
-    const float t = a->t_grid_host[i];
-    const float dt = a->t_grid_host[i + 1] - t;
-    float* traj = a->trajectory ? a->trajectory + (int64_t)(i + 1) * state : nullptr;
-    PROF(LEMAS_PROF_CFG_EULER);
-    LEMAS_TRY(lemas_cfg_euler(b.pred, 128, a->y, b.x16, 128, variants, traj, rows, c.mel_dim, t, dt,
-                              variants == 2 ? a->cfg_strength : 0.f, st));
+
+  const bool want_graph = a->use_graph && !e->profile && a->steps >= 3 && a->trajectory == nullptr;
+  if (!want_graph) {
+    for (int i = 0; i < a->steps; ++i) LEMAS_TRY(ode_step(e, b, a, variants, kv2, a->y, st));
+    return LEMAS_OK;
   }
+
+  // graph path: the ODE state lives in the workspace so that the captured pointers stay valid across calls
+  LEMAS_CUDA_OK(cudaMemcpyAsync(b.y_state, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
+  lemas_engine::StepGraph* g = nullptr;
+  for (auto& cand : e->graphs)
+    if (cand.batch == a->batch && cand.seq == a->seq && cand.variants == variants && cand.has_kv == (kv2 != nullptr) &&
+        cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope)
+      g = &cand;
+  int first_replayed = 0;
+  if (!g) {
+    // step 0 runs eagerly (it also performs every one-time kernel attribute set-up), then the step is captured
+    LEMAS_TRY(ode_step(e, b, a, variants, kv2, b.y_state, st));
+    first_replayed = 1;
+    const int64_t before = launches_so_far();
+    cudaGraph_t graph = nullptr;
+    if (!e->cap_stream) LEMAS_CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    LEMAS_CUDA_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = ode_step(e, b, a, variants, kv2, b.y_state, e->cap_stream);
+    const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+    const int nodes = (int)(launches_so_far() - before);
+    count_launches(-nodes);  // capturing launched nothing
+    if (rc != LEMAS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    LEMAS_CUDA_OK(ce);
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LEMAS_CUDA_OK(ie);
+    if (e->graphs.size() >= 8) {  // bounded cache: drop the oldest entry
+      cudaGraphExecDestroy(e->graphs.front().exec);
+      e->graphs.erase(e->graphs.begin());
+    }
+    e->graphs.push_back({a->batch, a->seq, variants, kv2 != nullptr, a->trajectory != nullptr, a->cfg_strength,
+                         a->workspace, a->rope, a->trajectory, exec, nodes});
+    g = &e->graphs.back();
+  }
+  for (int i = first_replayed; i < a->steps; ++i) {
+    LEMAS_CUDA_OK(cudaGraphLaunch(g->exec, st));
+    count_launches(g->nodes);
+  }
+  LEMAS_CUDA_OK(cudaMemcpyAsync(a->y, b.y_state, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
   return LEMAS_OK;
 }
 
