@@ -216,6 +216,100 @@ class BenchConfig:
 CONFIGS = {
     "C1": BenchConfig("C1", 1, 376, 940, 150, 16, 2.0, 5.0, 0),
     "C2": BenchConfig("C2", 1, 937, 2187, 350, 32, 2.0, 5.0, 0),
+    "C3": BenchConfig("C3", 32, 938, 0, 450, 32, 2.0, 3.0, 1),   # ragged: see c3_batch(); total_frames = max duration
     "C4": BenchConfig("C4", 256, 256, 768, 120, 32, 2.0, 3.0, 2),
     "C5": BenchConfig("C5", 1, 2813, 2814, 450, 64, 5.0, 3.0, 3),
 }
+
+
+def c3_batch(batch: int = 32, seed: int = 1, samples: int = 240_000, vocab: int = 898):
+    """Config C3 (BASELINE.json configs[2]): mixed-length utterances with raw 10 s reference audio,
+    lens ~ U{281..937} frames, ref tokens ~ U{45..150}, gen tokens ~ U{100..300},
+    duration_b = lens_b + int(lens_b / ref_b * gen_b) (utils_infer.py:520-527), clamped to 4096 (cfm.py:304)."""
+    g = _gen(5000 + seed)
+    lens = torch.randint(281, 938, (batch,), generator=g)
+    ref_t = torch.randint(45, 151, (batch,), generator=g)
+    gen_t = torch.randint(100, 301, (batch,), generator=g)
+    dur = torch.tensor([min(4096, int(l) + int(int(l) / int(r) * int(n))) for l, r, n in zip(lens, ref_t, gen_t)])
+    n_tok = (ref_t + gen_t).tolist()
+    text = synthetic_text_ids(batch, max(n_tok), vocab, seed=seed, lengths=n_tok)
+    audio = synthetic_ref_audio(batch, samples, seed=seed)
+    return dict(audio=audio, text=text, lens=lens, duration=dur)
+
+
+# ----------------------------------------------------------------------------- prosody encoder (config C3)
+
+# `pretssel_cfg.json` keys the reference reads (prosody_encoder.py:387-400); values = Pretssel defaults (SURVEY.md §8d).
+PROSODY_CFG = dict(prosody_channels=[512, 512, 512, 512, 1536], prosody_kernel_sizes=[5, 3, 3, 3, 1],
+                   prosody_dilations=[1, 2, 3, 4, 1], prosody_attention_channels=128, prosody_res2net_scale=8,
+                   prosody_se_channels=128, prosody_global_context=True, prosody_groups=[1, 1, 1, 1, 3],
+                   prosody_embed_dim=512, input_feat_per_channel=80)
+# reduced width for fast CPU tests (embed dim stays 512: prosody_to_mel / prosody_text_proj are Linear(512, .))
+TINY_PROSODY_CFG = dict(PROSODY_CFG, prosody_channels=[64, 64, 64, 64, 192], prosody_attention_channels=32,
+                        prosody_se_channels=32)
+
+
+def prosody_param_shapes(cfg: dict) -> dict[str, tuple]:
+    """Parameter names and shapes of the reference ECAPA_TDNN (prosody_encoder.py:30-132) for a pretssel cfg."""
+    ch, ks, gr = cfg["prosody_channels"], cfg["prosody_kernel_sizes"], cfg["prosody_groups"]
+    scale, se, att = cfg["prosody_res2net_scale"], cfg["prosody_se_channels"], cfg["prosody_attention_channels"]
+    shapes: dict[str, tuple] = {}
+
+    def tdnn(prefix, cin, cout, k, g=1):
+        shapes[prefix + "conv.weight"] = (cout, cin // g, k)
+        shapes[prefix + "conv.bias"] = (cout,)
+        shapes[prefix + "norm.weight"] = (cout,)
+        shapes[prefix + "norm.bias"] = (cout,)
+
+    def conv(prefix, cin, cout):
+        shapes[prefix + "weight"] = (cout, cin, 1)
+        shapes[prefix + "bias"] = (cout,)
+
+    tdnn("blocks.0.", cfg["input_feat_per_channel"], ch[0], ks[0], gr[0])
+    for i in range(1, len(ch) - 1):
+        q = f"blocks.{i}."
+        tdnn(q + "tdnn1.", ch[i - 1], ch[i], 1, gr[i])
+        for j in range(scale - 1):
+            tdnn(q + f"res2net_block.blocks.{j}.", ch[i] // scale, ch[i] // scale, ks[i])
+        tdnn(q + "tdnn2.", ch[i], ch[i], 1, gr[i])
+        conv(q + "se_block.conv1.", ch[i], se)
+        conv(q + "se_block.conv2.", se, ch[i])
+        if ch[i - 1] != ch[i]:
+            conv(q + "shortcut.", ch[i - 1], ch[i])
+    tdnn("mfa.", ch[-1], ch[-1], ks[-1], gr[-1])
+    tdnn("asp.tdnn.", ch[-1] * (3 if cfg["prosody_global_context"] else 1), att, 1)
+    conv("asp.conv.", att, ch[-1])
+    shapes["asp_norm.weight"] = (2 * ch[-1],)
+    shapes["asp_norm.bias"] = (2 * ch[-1],)
+    conv("fc.", 2 * ch[-1], cfg["prosody_embed_dim"])
+    return shapes
+
+
+def make_prosody_state_dict(cfg: dict = PROSODY_CFG, seed: int = 13) -> dict[str, torch.Tensor]:
+    """ECAPA-TDNN weights under the reference's module names.  Every tensor is drawn from its own generator seeded by
+    (seed, key), so the values do not depend on enumeration order."""
+    import zlib
+
+    sd = {}
+    for key, shape in prosody_param_shapes(cfg).items():
+        g = _gen(seed * 1_000_003 + zlib.crc32(key.encode()))
+        if key.endswith("norm.weight"):
+            sd[key] = 1.0 + _normal(g, shape, 0.1)
+        elif key.endswith("bias"):
+            sd[key] = _normal(g, shape, 0.05)
+        else:  # conv weights [out, in/groups, k]
+            sd[key] = _normal(g, shape, 1.0 / math.sqrt(shape[1] * shape[2]))
+    return sd
+
+
+def write_prosody_assets(directory, cfg: dict = PROSODY_CFG, seed: int = 13):
+    """pretssel_cfg.json + prosody_encoder checkpoint (keys prefixed `prosody_encoder.` like the released file)."""
+    import json
+    from pathlib import Path
+
+    d = Path(directory)
+    d.mkdir(parents=True, exist_ok=True)
+    cfg_path, ckpt_path = d / "pretssel_cfg.json", d / "prosody_encoder_UnitY2.pt"
+    cfg_path.write_text(json.dumps({"model": cfg}))
+    torch.save({"prosody_encoder." + k: v for k, v in make_prosody_state_dict(cfg, seed).items()}, ckpt_path)
+    return cfg_path, ckpt_path

@@ -108,6 +108,56 @@ def run_sample_case(case: dict) -> dict:
                 in_sums=torch.tensor([checksum(cond), checksum(noise), float(text.sum())], dtype=torch.float64))
 
 
+PROSODY_CASE = dict(name="sample_tiny_prosody", wseed=17, pseed=13, seed=6, batch=2, samples=12000, n_text=24,
+                    text_lens=[24, 15], lens=[47, 30], durations=[110, 75], steps=3, cfg=2.0, sway=3.0)
+
+
+def prosody_case_inputs(case: dict):
+    """Shared with tests/golden_cases.py."""
+    import dataclasses
+
+    arch = dataclasses.replace(syn.TINY_ARCH, use_prosody_encoder=True)
+    audio = syn.synthetic_ref_audio(case["batch"], case["samples"], seed=case["seed"])
+    text = syn.synthetic_text_ids(case["batch"], case["n_text"], arch.text_num_embeds, seed=case["seed"],
+                                  lengths=case["text_lens"])
+    noise = syn.synthetic_noise(case["durations"], arch.mel_dim, seed=case["seed"])
+    return arch, audio, text, noise
+
+
+def run_prosody_case(case: dict, tmp: Path) -> dict:
+    """CFM.sample from RAW AUDIO with the prosody encoder on (config C3's path), both use_acc_grl settings."""
+    arch, audio, text, noise = prosody_case_inputs(case)
+    paths = syn.write_prosody_assets(tmp, syn.TINY_PROSODY_CFG, seed=case["pseed"])
+    sd = syn.make_dit_state_dict(arch, seed=case["wseed"])
+    sd.update({"prosody_encoder.encoder." + k: v for k, v in
+               syn.make_prosody_state_dict(syn.TINY_PROSODY_CFG, case["pseed"]).items()})
+    model = verbatim.build_reference_cfm(arch, sd, prosody_paths=paths)
+    res = {}
+    real_randn = torch.randn
+    for grl in (False, True):
+        queue = [noise[b, : case["durations"][b]].clone() for b in range(case["batch"])]
+        torch.randn = lambda *size, **kw: queue.pop(0)
+        try:
+            out, traj = model.sample(cond=audio, text=text, duration=torch.tensor(case["durations"]),
+                                     lens=torch.tensor(case["lens"]), steps=case["steps"], cfg_strength=case["cfg"],
+                                     sway_sampling_coef=case["sway"], use_acc_grl=grl, use_prosody_encoder=True)
+        finally:
+            torch.randn = real_randn
+        res[f"out_grl{int(grl)}"] = out.clone()
+        res[f"last_grl{int(grl)}"] = traj[-1].clone()
+    # the embeddings themselves (cfm.py:248-262), to pin the ECAPA-TDNN restatement alone
+    import torchaudio
+    from lemas_tts.model.backbones.prosody_encoder import extract_fbank_16k
+
+    embeds = []
+    for b in range(case["batch"]):
+        a16 = torchaudio.functional.resample(audio[b:b + 1], 24000, 16000).squeeze(0)
+        embeds.append(model.prosody_encoder(extract_fbank_16k(a16).unsqueeze(0))[0])
+    res["embeds"] = torch.stack(embeds).detach().clone()
+    res["in_sums"] = torch.tensor([checksum(audio), checksum(noise), float(text.sum())], dtype=torch.float64)
+    return res
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     manifest = {"generator": "oracle/gen_golden.py", "reference": "/root/reference (verbatim import)",
@@ -118,6 +168,15 @@ def main():
         torch.save(res, GOLDEN / f"{case['name']}.pt")
         manifest["cases"].append(case)
         print(case["name"], {k: tuple(v.shape) for k, v in res.items()}, "out|sum|=%.6f" % checksum(res["out"]))
+
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        with torch.no_grad():
+            res = run_prosody_case(PROSODY_CASE, Path(tmp))
+    torch.save(res, GOLDEN / f"{PROSODY_CASE['name']}.pt")
+    manifest["prosody_case"] = PROSODY_CASE
+    print(PROSODY_CASE["name"], {k: tuple(v.shape) for k, v in res.items()})
 
     # mel front-end (modules.py:75-101) on synthetic audio
     verbatim.install()

@@ -96,8 +96,9 @@ def install() -> None:
     stub("pypinyin", lazy_pinyin=None, Style=None)
 
 
-def build_reference_cfm(arch, state_dict, vocab_char_map=None):
-    """Instantiate the reference CFM(DiT(...)) and strict-load a synthetic state dict (fp32, CPU)."""
+def build_reference_cfm(arch, state_dict, vocab_char_map=None, prosody_paths=None):
+    """Instantiate the reference CFM(DiT(...)) and strict-load a synthetic state dict (fp32, CPU).
+    prosody_paths = (pretssel_cfg.json, checkpoint) builds the reference ProsodyEncoder too."""
     install()
     from lemas_tts.model.cfm import CFM  # noqa: the reference's file
     from lemas_tts.model.backbones.dit import DiT
@@ -109,6 +110,9 @@ def build_reference_cfm(arch, state_dict, vocab_char_map=None):
                              target_sample_rate=24000, mel_spec_type="vocos"),
         odeint_kwargs=dict(method="euler"),
         vocab_char_map=vocab_char_map,
+        use_prosody_encoder=prosody_paths is not None,
+        prosody_cfg_path=None if prosody_paths is None else str(prosody_paths[0]),
+        prosody_ckpt_path=None if prosody_paths is None else str(prosody_paths[1]),
     )
     model.load_state_dict(state_dict, strict=True)
     return model.eval()

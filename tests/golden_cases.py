@@ -37,3 +37,19 @@ def inputs(case: dict):
         edit_mask[:, case["edit"][0]: case["edit"][1]] = False
     return dict(arch=arch, cond=cond, text=text, durations=durations, noise=noise, lens=lens,
                 duration=duration, edit_mask=edit_mask)
+
+
+PROSODY_CASE = MANIFEST.get("prosody_case")
+
+
+def prosody_inputs(case: dict):
+    """Same derivation as oracle/gen_golden.py:prosody_case_inputs."""
+    import dataclasses
+
+    arch = dataclasses.replace(syn.TINY_ARCH, use_prosody_encoder=True)
+    audio = syn.synthetic_ref_audio(case["batch"], case["samples"], seed=case["seed"])
+    text = syn.synthetic_text_ids(case["batch"], case["n_text"], arch.text_num_embeds, seed=case["seed"],
+                                  lengths=case["text_lens"])
+    noise = syn.synthetic_noise(case["durations"], arch.mel_dim, seed=case["seed"])
+    sd = syn.make_dit_state_dict(arch, seed=case["wseed"])
+    return arch, audio, text, noise, sd

@@ -118,3 +118,24 @@ head:
     v = Vocos.from_hparams(str(cfg))
     v.load_state_dict(syn.make_vocos_state_dict(), strict=True)
     assert sum(p.numel() for p in v.parameters()) == 13_531_650 or sum(p.numel() for p in v.parameters()) > 13e6
+
+
+def test_prosody_encoder_matches_reference(tmp_path):
+    """ECAPA-TDNN restatement (torch, host side) vs embeddings minted from the verbatim reference module."""
+    import torchaudio
+
+    from lemas_tts.model.backbones.prosody_encoder import ProsodyEncoder, extract_fbank_16k
+
+    case = gc.PROSODY_CASE
+    gold = gc.load(case["name"])
+    _, audio, _, _, _ = gc.prosody_inputs(case)
+    cfg_path, ckpt_path = syn.write_prosody_assets(tmp_path, syn.TINY_PROSODY_CFG, seed=case["pseed"])
+    enc = ProsodyEncoder(cfg_path, ckpt_path).eval()
+    with torch.no_grad():
+        for b in range(case["batch"]):
+            a16 = torchaudio.functional.resample(audio[b:b + 1], 24000, 16000).squeeze(0)
+            emb = enc(extract_fbank_16k(a16).unsqueeze(0))[0]
+            assert (emb - gold["embeds"][b]).abs().max() < 1e-5
+            assert abs(float(emb.norm()) - 1.0) < 1e-5
+    full = syn.make_prosody_state_dict(syn.PROSODY_CFG)
+    assert abs(sum(v.numel() for v in full.values()) - 5.6e6) < 0.1e6  # Pretssel-sized encoder

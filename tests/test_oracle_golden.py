@@ -78,3 +78,21 @@ def test_edit_mask_keeps_reference_region_bit_exact():
     keep = torch.ones(150, dtype=torch.bool)
     keep[case["edit"][0]: case["edit"][1]] = False
     assert torch.equal(gold["out"][0, :150][keep], inp["cond"][0][keep])
+
+
+def test_prosody_conditioning_matches_reference():
+    """Config C3's path (raw-audio cond, prosody encoder on): the oracle's conditioning algebra (prosody_to_mel added
+    after zero padding, use_acc_grl taking the pre-prosody mel, prosody_text_proj on both CFG variants) against the
+    verbatim reference; the embeddings themselves come from the fixture (the ECAPA-TDNN is pinned separately in
+    tests/test_host_cpu.py)."""
+    case = gc.PROSODY_CASE
+    gold = gc.load(case["name"])
+    arch, audio, text, noise, sd = gc.prosody_inputs(case)
+    mel = orc.mel_spectrogram(audio).permute(0, 2, 1)
+    for grl in (False, True):
+        out, traj = orc.cfm_sample(sd, arch, mel, text, torch.tensor(case["durations"]), lens=torch.tensor(case["lens"]),
+                                   steps=case["steps"], cfg_strength=case["cfg"], sway_sampling_coef=case["sway"],
+                                   noise=noise, use_acc_grl=grl, prosody_embeds=gold["embeds"])
+        assert (traj[-1] - gold[f"last_grl{int(grl)}"]).abs().max() < TOL * 5
+        assert (out - gold[f"out_grl{int(grl)}"]).abs().max() < TOL * 5
+    assert (gold["out_grl0"] - gold["out_grl1"]).abs().max() > 1e-2, "the two settings must differ for the test to bite"

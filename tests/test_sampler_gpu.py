@@ -147,3 +147,30 @@ def test_cpu_model_fails_loudly():
     model = CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"))
     with pytest.raises(RuntimeError, match="CUDA error"):
         model.sample(cond=torch.zeros(1, 10, 100), text=torch.zeros(1, 4, dtype=torch.long), duration=20, steps=2)
+
+
+def test_prosody_path_from_raw_audio_matches_reference_golden(tmp_path):
+    """Config C3's path: raw-audio conditioning (mel on device), prosody encoder on, ragged batch, both use_acc_grl
+    settings — against the verbatim reference."""
+    from lemas_tts.model.backbones.dit import DiT
+    from lemas_tts.model.cfm import CFM
+
+    case = gc.PROSODY_CASE
+    gold = gc.load(case["name"])
+    arch, audio, text, noise, sd = gc.prosody_inputs(case)
+    cfg_path, ckpt_path = syn.write_prosody_assets(tmp_path, syn.TINY_PROSODY_CFG, seed=case["pseed"])
+    model = CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"),
+                use_prosody_encoder=True, prosody_cfg_path=str(cfg_path), prosody_ckpt_path=str(ckpt_path))
+    sd = dict(sd)
+    sd.update({"prosody_encoder.encoder." + k: v for k, v in
+               syn.make_prosody_state_dict(syn.TINY_PROSODY_CFG, case["pseed"]).items()})
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    valid = torch.arange(max(case["durations"]))[None] < torch.tensor(case["durations"])[:, None]
+    for grl in (False, True):
+        out, traj = model.sample(cond=audio.cuda(), text=text.cuda(), duration=torch.tensor(case["durations"]).cuda(),
+                                 lens=torch.tensor(case["lens"]).cuda(), steps=case["steps"], cfg_strength=case["cfg"],
+                                 sway_sampling_coef=case["sway"], noise=noise, use_acc_grl=grl,
+                                 use_prosody_encoder=True)
+        _check(out.cpu()[valid], gold[f"out_grl{int(grl)}"][valid], f"prosody grl={grl} out")
+        _check(traj[-1].cpu()[valid], gold[f"last_grl{int(grl)}"][valid], f"prosody grl={grl} final state")
