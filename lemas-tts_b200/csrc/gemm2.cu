@@ -45,60 +45,88 @@ constexpr int G2_SMEM = G2_OFF_BAR + 256 + 1024;
 
 DEVI uint2 pack4_half(float4 v) { return make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w)); }
 
-// One 32-row x 32-column block of the accumulator.  r[i] = acc[row_base + lane][col0 + i].
-// bias4 / gate4: this thread's 4 columns (col0 + 4*(lane&7) ..) of the per-column vectors, loaded by the caller at
-// tile start so their latency hides behind the main loop.  All global loads of the block are issued before any
-// dependent math or store — the compiler will not hoist them across the stores on its own.
+// Row bookkeeping of one epilogue warp: 32 consecutive rows of ONE batch item (tiles never straddle batch items, so
+// no per-row division is needed and sequence positions of a warp start at a multiple of 32).
+struct RowCtx {
+  int b;          // batch item
+  int pos0;       // sequence position of the warp's first row
+  int nrows;      // valid rows of the warp (<= 32; rows beyond the sequence are skipped)
+  long grow0;     // global row of the warp's first row = b * rows + pos0
+};
+
+// Global loads a 32 x 32 block needs besides the accumulator (residual rows / RoPE cos,sin), fetched one block
+// ahead of its use so that their L2 latency overlaps the previous block's math and stores.
 template <int EPI>
-DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], int row_base, int col0, int lane,
-                     float4 bias4, float4 gate4) {
-  const int M = p.rows;
+DEVI void epi2_prefetch(const GemmParams& p, const RowCtx& rc, int col0, int lane, float4 (&pre)[8]) {
+  const int c4 = lane & 7, rsub = lane >> 3;
+  const int col = col0 + c4 * 4;
+  if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rr = it * 4 + rsub;
+      if (rr < rc.nrows) pre[it] = *reinterpret_cast<const float4*>(p.resid + (rc.grow0 + rr) * p.ldr + col);
+    }
+  } else if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
+    if (col0 < 2 * p.inner) {
+      const int within = col % p.inner;
+      const bool rot = within < p.rope_cols;
+      const int pair0 = (within & 63) >> 1;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rsub;
+        pre[it] = make_float4(1.f, 0.f, 1.f, 0.f);
+        if (rot && rr < rc.nrows)
+          pre[it] = __ldg(reinterpret_cast<const float4*>(p.rope + (long)(rc.pos0 + rr) * 32 + pair0));
+      }
+    }
+  }
+}
+
+// One 32-row x 32-column block of the accumulator.  r[i] = acc[row lane of the warp][col0 + i].
+// bias4 / gate4: this thread's 4 columns (col0 + 4*(lane&7) ..) of the per-column vectors.
+template <int EPI>
+DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], const RowCtx& rc, int col0, int lane,
+                     float4 bias4, float4 gate4, const float4 (&pre)[8]) {
   if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
-    if (col0 >= 2 * p.inner) {  // V: transposed copy [b, head, d, pos]; lanes = consecutive positions
-      const int grow = row_base + lane;
+    if (col0 >= 2 * p.inner) {
+      // V: transposed copy vt[b, head, d, pos].  The block is transposed through shared memory as fp16 so that each
+      // lane stores 8 consecutive positions (16 B) of one head-dim row instead of 32 scattered 2-byte stores.
+      const int vcol = col0 - 2 * p.inner;
+      const int heads = p.inner >> 6;
+      __half* sth = reinterpret_cast<__half*>(stg);  // [32 d][40 pos] halves (80 B rows: conflict-free 16 B reads)
       float4 bv[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (grow < M) {
-        const int b = grow / p.seq_len, pos = grow - b * p.seq_len;
-        const int vcol = col0 - 2 * p.inner;
-        const int heads = p.inner >> 6;
-        __half* dst = p.vt + ((long)(b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * p.vt_ld + pos;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dst[(long)(4 * j + 0) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 0]) + bv[j].x);
-          dst[(long)(4 * j + 1) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 1]) + bv[j].y);
-          dst[(long)(4 * j + 2) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 2]) + bv[j].z);
-          dst[(long)(4 * j + 3) * p.vt_ld] = __float2half_rn(__uint_as_float(r[4 * j + 3]) + bv[j].w);
+      for (int j = 0; j < 8; ++j) {
+        sth[(4 * j + 0) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 0]) + bv[j].x);
+        sth[(4 * j + 1) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 1]) + bv[j].y);
+        sth[(4 * j + 2) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 2]) + bv[j].z);
+        sth[(4 * j + 3) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 3]) + bv[j].w);
+      }
+      __syncwarp();
+      __half* dst0 = p.vt + ((long)(rc.b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * p.vt_ld + rc.pos0;
+      const int oct = lane & 3, dsub = lane >> 2;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int d = it * 8 + dsub;
+        const uint4 v = *reinterpret_cast<const uint4*>(sth + d * 40 + oct * 8);
+        __half* dst = dst0 + (long)d * p.vt_ld + oct * 8;
+        if (oct * 8 + 8 <= rc.nrows) {
+          *reinterpret_cast<uint4*>(dst) = v;  // pos0 % 32 == 0 and vt_ld % 8 == 0: 16-byte aligned
+        } else {
+          const __half* hv = reinterpret_cast<const __half*>(&v);
+          for (int i = 0; i < 8; ++i)
+            if (oct * 8 + i < rc.nrows) dst[i] = hv[i];
         }
       }
+      __syncwarp();
       return;
     }
   }
   const int c4 = lane & 7, rsub = lane >> 3;
   const int col = col0 + c4 * 4;
-
-  // ---- global loads of this block, issued up front
-  [[maybe_unused]] float4 pre[8];
-  if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int grow = row_base + it * 4 + rsub;
-      if (grow < M) pre[it] = *reinterpret_cast<const float4*>(p.resid + (long)grow * p.ldr + col);
-    }
-  } else if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
-    const int within = col % p.inner;
-    const bool rot = within < p.rope_cols;
-    const int pair0 = (within & 63) >> 1;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int grow = row_base + it * 4 + rsub;
-      pre[it] = make_float4(1.f, 0.f, 1.f, 0.f);
-      if (rot && grow < M)
-        pre[it] = __ldg(reinterpret_cast<const float4*>(p.rope + (long)(grow % p.seq_len) * 32 + pair0));
-    }
-  }
 
   // ---- transpose through shared memory: lane-per-row -> 8 lanes per row
   float4* srow = reinterpret_cast<float4*>(stg + lane * G2_PITCH);
@@ -111,35 +139,34 @@ DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], i
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int rr = it * 4 + rsub;
-    const int grow = row_base + rr;
-    if (grow >= M) continue;
+    if (rr >= rc.nrows) continue;
+    const long grow = rc.grow0 + rr;
     float4 v = *reinterpret_cast<const float4*>(stg + rr * G2_PITCH + c4 * 4);
     v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
     if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
-      const int b = grow / p.seq_len;
       float4 g = gate4;
       if (p.gate != nullptr && p.gate_bstride != 0)
-        g = __ldg(reinterpret_cast<const float4*>(p.gate + (long)b * p.gate_bstride + col));
-      const bool dead = p.row_valid != nullptr && (grow - b * p.seq_len) >= __ldg(p.row_valid + b);
+        g = __ldg(reinterpret_cast<const float4*>(p.gate + (long)rc.b * p.gate_bstride + col));
+      const bool dead = p.row_valid != nullptr && (rc.pos0 + rr) >= __ldg(p.row_valid + rc.b);
       float4 o = pre[it];
       if (!dead) { o.x += g.x * v.x; o.y += g.y * v.y; o.z += g.z * v.z; o.w += g.w * v.w; }
-      *reinterpret_cast<float4*>(p.out32 + (long)grow * p.ld32 + col) = o;
+      *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + col) = o;
     } else if constexpr (EPI == LEMAS_EPI_BIAS_F16) {
-      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+      *reinterpret_cast<uint2*>(p.out16 + grow * p.ld16 + col) = pack4_half(v);
     } else if constexpr (EPI == LEMAS_EPI_GELU_TANH_F16) {
       v.x = gelu_tanh_f(v.x); v.y = gelu_tanh_f(v.y); v.z = gelu_tanh_f(v.z); v.w = gelu_tanh_f(v.w);
-      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+      *reinterpret_cast<uint2*>(p.out16 + grow * p.ld16 + col) = pack4_half(v);
     } else if constexpr (EPI == LEMAS_EPI_GELU_ERF_F16) {
       v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w);
-      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+      *reinterpret_cast<uint2*>(p.out16 + grow * p.ld16 + col) = pack4_half(v);
     } else if constexpr (EPI == LEMAS_EPI_BIAS_F32) {
-      *reinterpret_cast<float4*>(p.out32 + (long)grow * p.ld32 + col) = v;
+      *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + col) = v;
     } else if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {  // q | k columns (V handled above); cs = (cos0, sin0, cos1, sin1)
       const float4 cs = pre[it];
       const float x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
       v.x = x0 * cs.x - x1 * cs.y; v.y = x1 * cs.x + x0 * cs.y;
       v.z = x2 * cs.z - x3 * cs.w; v.w = x3 * cs.z + x2 * cs.w;
-      *reinterpret_cast<uint2*>(p.out16 + (long)grow * p.ld16 + col) = pack4_half(v);
+      *reinterpret_cast<uint2*>(p.out16 + grow * p.ld16 + col) = pack4_half(v);
     }
   }
   __syncwarp();  // the staging buffer is rewritten by the next block
@@ -162,9 +189,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int m_tiles = (p.rows + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int m_tiles_b = (p.rows + 2 * G2_BM - 1) / (2 * G2_BM);  // per batch item: tiles never straddle items
   const int n_tiles = p.n / G2_BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int num_tiles = p.batches * m_tiles_b * n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -191,14 +218,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int n_idx = tile % n_tiles;
-        const int m0 = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM;
+        const int mt = tile / n_tiles;
+        const int bi = mt / m_tiles_b;
+        const int m0 = (mt - bi * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM;
         const int n0 = n_idx * G2_BN + (int)rank * (G2_BN / 2);
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);
           const uint32_t full_leader = mapa_shared(smem_u32(full_bar + stage), 0);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-          tma_load_2d_pair(sa, &tmA, full_leader, it * G2_BK, m0);
+          tma_load_3d_pair(sa, &tmA, full_leader, it * G2_BK, m0, bi);
           tma_load_2d_pair(sa + G2_A_BYTES, &tmW, full_leader, it * G2_BK, n0);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -243,7 +272,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int n_idx = tile % n_tiles;
-      const int row_base = (tile / n_tiles) * (2 * G2_BM) + (int)rank * G2_BM + sub * 32;
+      const int mt = tile / n_tiles;
+      RowCtx rc;
+      rc.b = mt / m_tiles_b;
+      rc.pos0 = (mt - rc.b * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM + sub * 32;
+      rc.nrows = min(32, p.rows - rc.pos0);
+      rc.grow0 = (long)rc.b * p.rows + rc.pos0;
       const int n0 = n_idx * G2_BN;
       // Per-column vectors (bias, gate) for this thread's 4 columns of each 32-column block are fetched one block
       // ahead; block 0's are issued before the accumulator wait so their latency hides behind the main loop.
@@ -260,19 +294,31 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
       const int j0 = half * 4;
       float4 bias_nxt = load_bias(j0), gate_nxt = load_gate(j0);
-      mbar_wait(acc_full + acc, acc_phase);
-      tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + acc * G2_BN;
-      if (row_base < p.rows) {
+      if (rc.nrows > 0) {
+        float4 pre_nxt[8];
+        epi2_prefetch<EPI>(p, rc, n0 + j0 * 32, lane, pre_nxt);  // does not depend on the accumulator either
+        mbar_wait(acc_full + acc, acc_phase);
+        tc_fence_after();
 #pragma unroll 1
         for (int j = j0; j < j0 + 4; ++j) {
           const float4 bias4 = bias_nxt, gate4 = gate_nxt;
-          if (j < j0 + 3) { bias_nxt = load_bias(j + 1); gate_nxt = load_gate(j + 1); }
+          float4 pre[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre[i] = pre_nxt[i];
+          if (j < j0 + 3) {
+            bias_nxt = load_bias(j + 1);
+            gate_nxt = load_gate(j + 1);
+            epi2_prefetch<EPI>(p, rc, n0 + (j + 1) * 32, lane, pre_nxt);
+          }
           uint32_t r[32];
           tmem_ld_32x32(t_addr + j * 32, r);
           tmem_ld_wait();
-          epi2_block<EPI>(p, stg, r, row_base, n0 + j * 32, lane, bias4, gate4);
+          epi2_block<EPI>(p, stg, r, rc, n0 + j * 32, lane, bias4, gate4, pre);
         }
+      } else {
+        mbar_wait(acc_full + acc, acc_phase);
+        tc_fence_after();
       }
       tc_fence_before();
       __syncwarp();
@@ -295,7 +341,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmPar
     LEMAS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
     configured = true;
   }
-  const int tiles = ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
+  const int tiles = p.batches * ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
   int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
   if (pairs < 1) pairs = 1;
   if (pairs > tiles) pairs = tiles;
@@ -308,18 +354,29 @@ bool gemm2_eligible(const lemas_gemm_desc& d) {
   const bool epi_ok = d.epilogue == LEMAS_EPI_BIAS_F16 || d.epilogue == LEMAS_EPI_QKV_ROPE ||
                       d.epilogue == LEMAS_EPI_GELU_TANH_F16 || d.epilogue == LEMAS_EPI_GELU_ERF_F16 ||
                       d.epilogue == LEMAS_EPI_GATE_RESID_F32 || d.epilogue == LEMAS_EPI_BIAS_F32;
-  return epi_ok && d.batches == 1 && d.taps == 1 && d.group_cols == 0 && d.block_n == 256 && d.n % G2_BN == 0 &&
+  return epi_ok && (d.batches == 1 || d.seq_len == d.rows) && d.taps == 1 && d.group_cols == 0 && d.block_n == 256 && d.n % G2_BN == 0 &&
          d.a_cols == d.k_per_tap && (d.bias == nullptr || (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0);
 }
 
 // Called by gemm_launch (gemm.cu) after validation, with the kernel parameters already filled in.
-int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p, cudaStream_t st) {
+int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p_in, cudaStream_t st) {
+  // A flat [rows, K] operand made of whole sequences (rows = batches * seq_len) is tiled per sequence, so that tiles
+  // never straddle batch items: the epilogues index per-batch vectors without dividing, and sequence positions of a
+  // warp's 32 rows start at a multiple of 32 (aligned 16-byte stores of the transposed V copy).
+  int batches = d.batches, rows = d.rows;
+  if (batches == 1 && d.seq_len > 0 && d.seq_len < rows && rows % d.seq_len == 0) {
+    batches = rows / d.seq_len;
+    rows = d.seq_len;
+  }
+  GemmParams p = p_in;
+  p.batches = batches;
+  p.rows = rows;
   CUtensorMap tmA, tmW;
   {
-    uint64_t dims[2] = {(uint64_t)d.a_cols, (uint64_t)d.rows};
-    uint64_t strides[1] = {(uint64_t)d.lda * 2};
-    uint32_t box[2] = {G2_BK, G2_BM};
-    LEMAS_TRY(make_tensor_map_f16(&tmA, d.a, 2, dims, strides, box));
+    uint64_t dims[3] = {(uint64_t)d.a_cols, (uint64_t)rows, (uint64_t)batches};
+    uint64_t strides[2] = {(uint64_t)d.lda * 2, (uint64_t)rows * d.lda * 2};
+    uint32_t box[3] = {G2_BK, G2_BM, 1};
+    LEMAS_TRY(make_tensor_map_f16(&tmA, d.a, 3, dims, strides, box));
   }
   {
     uint64_t dims[2] = {(uint64_t)d.ldw, (uint64_t)d.w_rows};
