@@ -265,7 +265,17 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     nv.require_device()
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at init; stdout must carry exactly one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     wl = Workload(args.workload, args.batch, seed_offset=100 * rank)  # every rank synthesises its own utterances
     cfg, batch = wl.cfg, wl.batch

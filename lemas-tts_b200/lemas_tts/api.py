@@ -89,7 +89,9 @@ class TTS:
     def __init__(self, model="multilingual", ckpt_file="", vocab_file="", ode_method="euler", use_ema=False,
                  vocoder_local_path=str(CKPTS_ROOT / "vocos-mel-24khz"), use_prosody_encoder=False,
                  prosody_cfg_path="", prosody_ckpt_path="", device=None, hf_cache_dir=None, frontend="phone"):
-        model_arc, mel_cfg = load_model_config(THIS_FILE.parent / "configs" / f"{model}.yaml")
+        # `model` names a bundled config (api.py:99); a path to a yaml of the same layout is accepted as well
+        cfg_file = Path(model) if str(model).endswith((".yaml", ".yml")) else THIS_FILE.parent / "configs" / f"{model}.yaml"
+        model_arc, mel_cfg = load_model_config(cfg_file)
         self.mel_spec_type = mel_cfg["mel_spec_type"]
         self.target_sample_rate = mel_cfg["target_sample_rate"]
         self.ode_method = ode_method
@@ -134,10 +136,9 @@ class TTS:
 
             sf.write(file_wave, wav, self.target_sample_rate)
         except ImportError:
-            import torch
-            import torchaudio
+            from lemas_tts.infer.utils_infer import save_audio
 
-            torchaudio.save(file_wave, torch.as_tensor(wav, dtype=torch.float32)[None], self.target_sample_rate)
+            save_audio(file_wave, wav, self.target_sample_rate)
         if remove_silence:
             remove_silence_for_generated_wav(file_wave)
 

@@ -27,6 +27,41 @@ except ImportError:  # pragma: no cover
     tqdm = None
 
 
+def load_audio(path):
+    """torchaudio.load, falling back to scipy's WAV reader when torchaudio has no decoding backend installed
+    (torchaudio >= 2.9 delegates to torchcodec).  Returns (float32 [channels, samples], sample_rate)."""
+    try:
+        return torchaudio.load(path)
+    except (ImportError, RuntimeError, OSError):
+        from scipy.io import wavfile
+
+        sr, data = wavfile.read(path)
+        x = torch.from_numpy(np.ascontiguousarray(data))
+        if x.dtype == torch.int16:
+            x = x.float() / 32768.0
+        elif x.dtype == torch.int32:
+            x = x.float() / 2147483648.0
+        elif x.dtype == torch.uint8:
+            x = (x.float() - 128.0) / 128.0
+        else:
+            x = x.float()
+        x = x[None] if x.dim() == 1 else x.t().contiguous()
+        return x, int(sr)
+
+
+def save_audio(path, wave, sample_rate):
+    """Write float32 [channels, samples] (or [samples]) as 16-bit PCM WAV; torchaudio when it can, else scipy."""
+    wave = torch.as_tensor(wave, dtype=torch.float32)
+    wave = wave[None] if wave.dim() == 1 else wave
+    try:
+        torchaudio.save(path, wave, sample_rate)
+    except (ImportError, RuntimeError, OSError):
+        from scipy.io import wavfile
+
+        pcm = (wave.clamp(-1, 1) * 32767.0).round().to(torch.int16).t().contiguous().numpy()
+        wavfile.write(path, int(sample_rate), pcm[:, 0] if pcm.shape[1] == 1 else pcm)
+
+
 def _find_repo_root(start: Path) -> Path:
     for p in [start, *start.parents]:
         if (p / "pretrained_models").is_dir():
@@ -259,13 +294,13 @@ def preprocess_ref_audio_text(ref_audio_orig, ref_text, clip_short=True, show_in
         aseg = aseg[: int(end * 1000)] + AudioSegment.silent(duration=50)
         aseg.export(out_path, format="wav")
     else:
-        wave, sr = torchaudio.load(ref_audio_orig)
+        wave, sr = load_audio(ref_audio_orig)
         if clip_short and wave.shape[-1] > 12 * sr:
             wave = wave[..., : 12 * sr]
             show_info("Audio is over 12s, clipping short. (3)")
         wave = remove_silence_edges(wave, sr)
         wave = torch.cat([wave, torch.zeros(wave.shape[0], int(0.05 * sr))], dim=-1)
-        torchaudio.save(out_path, wave, sr)
+        save_audio(out_path, wave, sr)
     ref_audio = out_path
 
     with open(ref_audio, "rb") as audio_file:
@@ -295,7 +330,7 @@ def infer_process(ref_audio, ref_text, gen_text, model_obj, vocoder, mel_spec_ty
                   use_prosody_encoder=True, ref_ratio=None, no_ref_audio=False, speed=speed, fix_duration=fix_duration,
                   device=device):
     """utils_infer.py:399-458: chunk the text (string input) and run infer_batch_process once."""
-    audio, sr = torchaudio.load(ref_audio)
+    audio, sr = load_audio(ref_audio)
     if type(ref_text) == str:
         secs = audio.shape[-1] / sr
         max_chars = int(len(ref_text.encode("utf-8")) / secs * (22 - secs))
