@@ -126,6 +126,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // prologue overlapped the previous kernel's tail; q/k/v are visible from here on
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + ATT_BN;   // + 64 * half
 
@@ -198,32 +200,50 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     float m_ref = -INFINITY;           // max the accumulators O_half / l are currently scaled by
     float l_run = 0.f;
-    uint8_t* prow = smem + ATT_OFF_P + half * (ATT_P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
+    // 32-bit shared-window addresses (one register each, immediates for the rest): the softmax loop is issue-bound,
+    // every instruction of address arithmetic or pointer conversion in it costs throughput
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t a_sfull = sb + ATT_OFF_BAR + 9 * 8, a_sempty = sb + ATT_OFF_BAR + 10 * 8;
+    const uint32_t a_pfull = sb + ATT_OFF_BAR + (11 + half) * 8, a_ofull = sb + ATT_OFF_BAR + (13 + half) * 8;
+    const uint32_t a_prow = sb + ATT_OFF_P + half * (ATT_P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t xor7 = (r & 7) << 4;
     const uint32_t t_s = tmem_s + lane_addr + half * 64;
     const uint32_t t_o = tmem_o + lane_addr + half * ATT_D;
 
+    // Warps whose 32 query rows all lie beyond the sequence (last query tile) keep the barrier protocol going but do
+    // no softmax work: their P rows only feed output rows that are never stored.
+    const bool rows_dead = q0 + sub * 32 >= p.seq;
     for (int j = 0; j < n_blocks; ++j) {
+      if (rows_dead) {
+        mbar_wait_lean(a_sfull, j & 1);
+        if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);  // never run a p_full phase ahead of the live warps
+        if (lane == 0) { mbar_arrive_s(a_sempty); mbar_arrive_s(a_pfull); }
+        continue;
+      }
       const int valid = min(max(kvl - j * ATT_BN - half * 64, 0), 64);  // keys of this half-block that exist
+#ifdef LEMAS_ATT_TRACE  // clock64 stamps of one CTA (tools/trace_att.py); costs ~8 % of the kernel, off by default
       const bool tr = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 32;
       long long* tp = p.trace + ((warp - 2) * 32 + j) * 8;
-      if (tr) tp[0] = clock64();
-      mbar_wait(s_full, j & 1);
-      if (tr) tp[1] = clock64();
+#define ATT_STAMP(i) do { if (tr) tp[i] = clock64(); } while (0)
+#else
+#define ATT_STAMP(i) do { } while (0)
+#endif
+      ATT_STAMP(0);
+      mbar_wait_lean(a_sfull, j & 1);
+      ATT_STAMP(1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld_32x32(t_s, s0);
       tmem_ld_32x32(t_s + 32, s1);
       tmem_ld_wait();
       tc_fence_before();
-      if (lane == 0) mbar_arrive(s_empty);  // S_j is in registers (tcgen05.wait::ld is warp-wide): S_{j+1} may land
-      if (tr) tp[2] = clock64();
+      if (lane == 0) mbar_arrive_s(a_sempty);  // S_j is in registers (tcgen05.wait::ld is warp-wide): S_{j+1} may land
+      ATT_STAMP(2);
 
       float mx = -INFINITY;
       if (valid == 64) {
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains, not one of 32
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], __uint_as_float(s0[i]), __uint_as_float(s1[i]));
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        for (int i = 0; i < 32; ++i) mx = fmax3f(mx, __uint_as_float(s0[i]), __uint_as_float(s1[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -239,7 +259,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         const float alpha = (m_ref == -INFINITY) ? 0.f : ex2f((m_ref - m_new) * c);
         l_run *= alpha;
         if (j > 0) {  // O_half holds the sum of blocks < j: rescale it in TMEM once P V_{j-1} has retired
-          mbar_wait(o_full + half, (j - 1) & 1);
+          mbar_wait_lean(a_ofull, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < ATT_D; cc += 8) {  // narrow chunks: S_j (64 registers) stays live across this
@@ -256,7 +276,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         m_ref = m_new;
       }
       const float mc = (m_ref == -INFINITY) ? 0.f : m_ref * c;
-      if (tr) tp[3] = clock64();
+      ATT_STAMP(3);
 
       // exp2 of the whole half-row into packed fp16 registers first; only then wait for the P buffer (free once
       // P V_{j-1} has read it) — waiting before the exponentials re-synchronised the four warps of a half every block
@@ -267,31 +287,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int col = 2 * i;
+          if (!kFull && col >= valid) {  // warp-uniform: masked key pairs cost no SFU work
+            pk[i] = 0u;
+            continue;
+          }
           float e0 = ex2f(fmaf(__uint_as_float(col < 32 ? s0[col & 31] : s1[col & 31]), c, -mc));
           float e1 = ex2f(fmaf(__uint_as_float(col + 1 < 32 ? s0[(col + 1) & 31] : s1[(col + 1) & 31]), c, -mc));
-          if (!kFull && col >= valid) e0 = 0.f;
           if (!kFull && col + 1 >= valid) e1 = 0.f;
           rs4[i & 3] += e0 + e1;
           pk[i] = pack_half2(e0, e1);
         }
       };
       if (valid == 64) exp_block(std::true_type{}); else exp_block(std::false_type{});
-      if (tr) tp[4] = clock64();
-      if (j > 0) mbar_wait(o_full + half, (j - 1) & 1);
-      if (tr) tp[5] = clock64();
+      ATT_STAMP(4);
+      if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);
+      ATT_STAMP(5);
 #pragma unroll
       for (int u = 0; u < 8; ++u)  // 16-byte units of the 128-byte (64 keys x fp16) swizzled row
-        *reinterpret_cast<uint4*>(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        sts128(a_prow + ((u << 4) ^ xor7), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       fence_proxy_async_smem();  // make the generic-proxy P stores visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + half);
-      if (tr) tp[6] = clock64();
+      if (lane == 0) mbar_arrive_s(a_pfull);
+      ATT_STAMP(6);
     }
 
     // ---- merge the two key halves and normalise
-    mbar_wait(o_full + 0, (n_blocks - 1) & 1);
-    mbar_wait(o_full + 1, (n_blocks - 1) & 1);
+    mbar_wait_lean(sb + ATT_OFF_BAR + 13 * 8, (n_blocks - 1) & 1);
+    mbar_wait_lean(sb + ATT_OFF_BAR + 14 * 8, (n_blocks - 1) & 1);
     tc_fence_after();
     float2* xch = reinterpret_cast<float2*>(smem + ATT_OFF_XCH);  // P buffer: free now that every P V has retired
     xch[half * ATT_BM + r] = make_float2(m_ref, l_run);
@@ -370,7 +393,7 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   p.heads = heads;
   p.inner = inner;
   dim3 grid((seq + ATT_BM - 1) / ATT_BM, heads, batch);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)stream>>>(tmQK, tmVT, p);
+  LEMAS_CUDA_OK(launch_pdl(attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, (cudaStream_t)stream, tmQK, tmVT, p));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

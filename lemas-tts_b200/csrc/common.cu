@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace lemas {
@@ -16,6 +17,15 @@ int fail(int code, const std::string& msg) {
 static std::atomic<int64_t> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launches_so_far() { return g_launches.load(); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LEMAS_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 int sm_count() {
   static int n = 0;

@@ -49,4 +49,25 @@ int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const uint
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// LEMAS_PDL=0 disables programmatic dependent launch (A/B measurements)
+bool pdl_enabled();
+
+// Launch with the programmatic-stream-serialization attribute: the kernel's prologue (barrier init, TMEM
+// allocation, descriptor prefetch, instruction fetch) overlaps the tail of the previous kernel in the stream; the
+// kernel calls pdl_wait() before its first global access.  Works eagerly and under stream capture.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace lemas

@@ -16,6 +16,8 @@ template <bool AFFINE>
 __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, const float* __restrict__ p0, const float* __restrict__ p1, int mod_bstride,
           __half* __restrict__ out16, float* __restrict__ out32, int rows, int dim, int seq_len, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -392,8 +394,8 @@ int lemas_ln_modulate(const float* x, const float* scale, const float* shift, in
                       int32_t rows, int32_t dim, int32_t seq_len, void* stream) {
   LEMAS_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_VEC, "lemas_ln_modulate: dim must be a multiple of 128, <= 1024");
   LEMAS_REQUIRE(rows > 0 && seq_len > 0, "lemas_ln_modulate: bad shape");
-  ln_kernel<false><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, mod_bstride, (__half*)out16,
-                                                                     nullptr, rows, dim, seq_len, 1e-6f);
+  LEMAS_CUDA_OK(launch_pdl(ln_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, x, scale, shift,
+                           mod_bstride, (__half*)out16, (float*)nullptr, rows, dim, seq_len, 1e-6f));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

@@ -211,6 +211,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();  // the next kernel in the stream may start its own prologue
+  pdl_wait();     // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -345,7 +347,7 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmPar
   int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
   if (pairs < 1) pairs = 1;
   if (pairs > tiles) pairs = tiles;
-  kern<<<2 * pairs, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, p);
+  LEMAS_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(G2_THREADS), G2_SMEM, st, tmA, tmW, p));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

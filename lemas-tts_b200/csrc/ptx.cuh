@@ -278,3 +278,32 @@ DEVI void tmem_st_32x32_x8(uint32_t taddr, const uint32_t (&r)[8]) {
                : "memory");
 }
 }  // namespace lemas
+
+namespace lemas {
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; it must execute pdl_wait() before it
+// touches global memory (the wait returns once the predecessor grid has completed and its writes are visible).
+// pdl_trigger() lets the successor of THIS kernel begin launching.  Both are no-ops without the attribute.
+DEVI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+DEVI void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+}  // namespace lemas
+
+namespace lemas {
+// Lean variants on 32-bit shared-window addresses, for hot loops: no generic->shared conversion per call, and the
+// wait has no spin bound (use only where another role of the same CTA keeps a bounded mbar_wait — a protocol bug
+// then still traps the kernel instead of hanging the GPU).
+DEVI void mbar_wait_lean(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LEMAS_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra LEMAS_WAIT_%=;\n\t}\n"
+      ::"r"(bar_addr), "r"(parity) : "memory");
+}
+DEVI void mbar_arrive_s(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+DEVI void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+}  // namespace lemas
