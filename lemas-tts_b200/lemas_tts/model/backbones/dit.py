@@ -50,12 +50,22 @@ class TextEmbedding(nn.Module):
         h = F.linear(h, blk.pwconv2.weight.float(), blk.pwconv2.bias.float())
         return x + h
 
-    def forward(self, text: torch.Tensor, seq_len: int, drop_text: bool = False) -> torch.Tensor:
+    def forward_pair(self, text: torch.Tensor, seq_len: int):
+        """Conditional and unconditional embeddings in ONE batched pass (rows [0,B) keep their ids, rows [B,2B) have
+        them dropped): every op of the block stack is per-sample, so this equals two separate calls."""
+        B = text.shape[0]
+        both = self.forward(torch.cat((text, text), 0), seq_len, drop_rows=B)
+        return both[:B].contiguous(), both[B:].contiguous()
+
+    def forward(self, text: torch.Tensor, seq_len: int, drop_text: bool = False, drop_rows: int | None = None) -> torch.Tensor:
         text = (text + 1)[:, :seq_len]
         text = F.pad(text, (0, seq_len - text.shape[1]), value=0)
         text_mask = text == 0  # taken before the ids are dropped (dit.py:56-60)
         if drop_text:
             text = torch.zeros_like(text)
+        elif drop_rows is not None:  # rows >= drop_rows are the unconditional copies
+            text = text.clone()
+            text[drop_rows:] = 0
         h = F.embedding(text, self.text_embed.weight.float())
         if self.extra_modeling:
             pos = torch.arange(seq_len, device=text.device).clamp(max=self.precompute_max_pos - 1)
@@ -167,8 +177,7 @@ class DiT(nn.Module):
     def text_embeds(self, text, seq_len, prosody_text=None, cache=True):
         """Both cached text embeddings (dit.py:212-233), prosody projection already added."""
         if not cache or self.text_cond is None:
-            tc = self.text_embed(text, seq_len, drop_text=False)
-            tu = self.text_embed(text, seq_len, drop_text=True)
+            tc, tu = self.text_embed.forward_pair(text, seq_len)
             if prosody_text is not None and self.use_prosody_encoder:
                 pt = F.linear(prosody_text.float(), self.prosody_text_proj.weight.float(),
                               self.prosody_text_proj.bias.float())

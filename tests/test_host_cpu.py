@@ -139,3 +139,13 @@ def test_prosody_encoder_matches_reference(tmp_path):
             assert abs(float(emb.norm()) - 1.0) < 1e-5
     full = syn.make_prosody_state_dict(syn.PROSODY_CFG)
     assert abs(sum(v.numel() for v in full.values()) - 5.6e6) < 0.1e6  # Pretssel-sized encoder
+
+
+def test_text_embedding_pair_equals_two_passes():
+    arch = syn.TINY_ARCH
+    model = _cfm(arch)
+    model.load_state_dict(syn.make_dit_state_dict(arch, seed=11), strict=True)
+    text = syn.synthetic_text_ids(3, 40, arch.text_num_embeds, seed=2, lengths=[40, 22, 35])
+    te = model.transformer.text_embed
+    tc, tu = te.forward_pair(text, 131)
+    assert torch.equal(tc, te(text, 131, drop_text=False)) and torch.equal(tu, te(text, 131, drop_text=True))
