@@ -32,7 +32,8 @@ int lemas_version(void);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMA kernels can run), else 0. */
 int lemas_device_supported(void);
 /* sizeof() of the ABI structs, for bindings to self-check their mirrors: 0 lemas_gemm_desc, 1 lemas_dit_config,
- * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights; else -1. */
+ * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights,
+ * 7 lemas_text_block, 8 lemas_text_weights; else -1. */
 int lemas_abi_sizeof(int which);
 /* Number of kernels this library has launched in the calling process since it was loaded (all entry points). */
 int64_t lemas_launch_count(void);
@@ -239,6 +240,32 @@ int64_t lemas_vocos_workspace_bytes(const lemas_vocos_weights* w, int32_t batch,
 /* Vocos.decode (utils_infer.py:549): mel fp32 [batch, in_ch, t] -> wav fp32 [batch, (t-1)*256]. */
 int lemas_vocos_decode(const lemas_vocos_weights* w, const float* mel, float* wav, int32_t batch, int32_t t,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Text embedding (dit.py:51-81 TextEmbedding.forward + ConvNeXtV2Block modules.py:241-269 + GRN modules.py:225-234):
+ * runs once per CFM.sample for the conditional and unconditional copies of the text (dit.py:212-220).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lemas_text_block {
+  const float* dw_w; const float* dw_b;       /* fp32 [7, dim] tap-major, [dim]      text_blocks.i.dwconv            */
+  const float* ln_w; const float* ln_b;       /* fp32 [dim]                          text_blocks.i.norm              */
+  const void* w1; const float* b1;            /* fp16 [inter, dim], fp32 [inter]     text_blocks.i.pwconv1           */
+  const float* grn_gamma; const float* grn_beta; /* fp32 [inter]                     text_blocks.i.grn               */
+  const void* w2; const float* b2;            /* fp16 [dim, inter], fp32 [dim]       text_blocks.i.pwconv2           */
+} lemas_text_block;
+
+typedef struct lemas_text_weights {
+  int32_t dim, inter, layers, mask_padding;
+  const float* table;                         /* fp32 [text_num_embeds + 1, dim]     text_embed.text_embed.weight    */
+  const float* pos;                           /* fp32 [4096, dim] cat(cos, sin) table (modules.py:196-207)           */
+  const lemas_text_block* blocks;             /* host array [layers]                                                 */
+} lemas_text_weights;
+
+int64_t lemas_text_workspace_bytes(const lemas_text_weights* w, int32_t batch, int32_t seq);
+/* ids: int32 [batch, seq], ALREADY shifted by +1, truncated / zero-padded to seq (0 = filler, dit.py:52-55);
+ * drop: uint8 [batch], 1 = unconditional copy (token ids replaced by 0 AFTER the filler mask is taken, dit.py:56-60);
+ * out: fp32 [batch, seq, dim]. */
+int lemas_text_embedding(const lemas_text_weights* w, const int32_t* ids, const uint8_t* drop, float* out, int32_t batch,
+                         int32_t seq, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

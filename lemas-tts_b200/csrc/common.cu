@@ -102,6 +102,8 @@ int lemas_abi_sizeof(int which) {
     case 4: return (int)sizeof(lemas_sample_args);
     case 5: return (int)sizeof(lemas_vocos_layer);
     case 6: return (int)sizeof(lemas_vocos_weights);
+    case 7: return (int)sizeof(lemas_text_block);
+    case 8: return (int)sizeof(lemas_text_weights);
   }
   return -1;
 }

@@ -74,6 +74,16 @@ class VocosWeights(C.Structure):
                 ("head_w", vp), ("head_b", vp)]
 
 
+class TextBlock(C.Structure):
+    _fields_ = [("dw_w", vp), ("dw_b", vp), ("ln_w", vp), ("ln_b", vp), ("w1", vp), ("b1", vp),
+                ("grn_gamma", vp), ("grn_beta", vp), ("w2", vp), ("b2", vp)]
+
+
+class TextWeights(C.Structure):
+    _fields_ = [("dim", i32), ("inter", i32), ("layers", i32), ("mask_padding", i32), ("table", vp), ("pos", vp),
+                ("blocks", C.POINTER(TextBlock))]
+
+
 # every symbol include/lemas_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "lemas_last_error": (C.c_char_p, []),
@@ -101,6 +111,8 @@ SIGNATURES = {
     "lemas_dit_forward": (C.c_int, [vp, C.POINTER(SampleArgs), f32, vp, vp, vp]),
     "lemas_vocos_workspace_bytes": (i64, [C.POINTER(VocosWeights), i32, i32]),
     "lemas_vocos_decode": (C.c_int, [C.POINTER(VocosWeights), vp, vp, i32, i32, vp, i64, vp]),
+    "lemas_text_workspace_bytes": (i64, [C.POINTER(TextWeights), i32, i32]),
+    "lemas_text_embedding": (C.c_int, [C.POINTER(TextWeights), vp, vp, vp, i32, i32, vp, i64, vp]),
 }
 
 

@@ -287,3 +287,60 @@ class VocosEngine:
         nv.check(nv.load().lemas_vocos_decode(C.byref(self._weights), nv.ptr(mel), nv.ptr(wav), B, T,
                                               nv.ptr(self._ws), self._ws.numel(), nv.stream()))
         return wav
+
+
+class TextEngine:
+    """Packed TextEmbedding weights (dit.py:34-81) + `lemas_text_embedding`."""
+
+    def __init__(self, sd: dict, *, text_dim: int, conv_layers: int, mask_padding: bool, device="cuda",
+                 prefix: str = "text_embed."):
+        nv.require_device()
+        self.device = dv = torch.device(device)
+        keep = self._keep = []
+
+        def hold(t):
+            keep.append(t)
+            return t
+
+        p = prefix
+        self.dim, self.layers = text_dim, conv_layers
+        w = nv.TextWeights()
+        w.dim, w.inter, w.layers, w.mask_padding = text_dim, 2 * text_dim, conv_layers, int(mask_padding)
+        w.table = nv.ptr(hold(_dev(sd[p + "text_embed.weight"], dv, f32)))
+        if conv_layers > 0:
+            inv = 1.0 / (10000.0 ** (torch.arange(0, text_dim, 2)[: text_dim // 2].float() / text_dim))
+            ang = torch.outer(torch.arange(4096), inv).float()
+            w.pos = nv.ptr(hold(_dev(torch.cat([ang.cos(), ang.sin()], dim=-1), dv, f32)))  # modules.py:196-207
+        blocks = (nv.TextBlock * max(conv_layers, 1))()
+        for i in range(conv_layers):
+            q = f"{p}text_blocks.{i}."
+            L = blocks[i]
+            w.inter = sd[q + "pwconv1.weight"].shape[0]
+            L.dw_w = nv.ptr(hold(_dev(sd[q + "dwconv.weight"].float()[:, 0].t(), dv, f32)))  # [7, dim]
+            L.dw_b = nv.ptr(hold(_dev(sd[q + "dwconv.bias"], dv, f32)))
+            L.ln_w = nv.ptr(hold(_dev(sd[q + "norm.weight"], dv, f32)))
+            L.ln_b = nv.ptr(hold(_dev(sd[q + "norm.bias"], dv, f32)))
+            L.w1 = nv.ptr(hold(_dev(sd[q + "pwconv1.weight"], dv, f16)))
+            L.b1 = nv.ptr(hold(_dev(sd[q + "pwconv1.bias"], dv, f32)))
+            L.grn_gamma = nv.ptr(hold(_dev(sd[q + "grn.gamma"].reshape(-1), dv, f32)))
+            L.grn_beta = nv.ptr(hold(_dev(sd[q + "grn.beta"].reshape(-1), dv, f32)))
+            L.w2 = nv.ptr(hold(_dev(sd[q + "pwconv2.weight"], dv, f16)))
+            L.b2 = nv.ptr(hold(_dev(sd[q + "pwconv2.bias"], dv, f32)))
+        self._blocks = blocks
+        w.blocks = blocks
+        self._weights = w
+        self._ws = None
+
+    def embed(self, ids: torch.Tensor, drop: torch.Tensor) -> torch.Tensor:
+        """ids: int32 [B, N] (shifted by +1, 0 = filler); drop: uint8 [B] -> fp32 [B, N, dim]."""
+        B, N = ids.shape
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        drop = drop.to(device=self.device, dtype=torch.uint8).contiguous()
+        need = int(nv.load().lemas_text_workspace_bytes(C.byref(self._weights), B, N))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        out = torch.empty(B, N, self.dim, device=self.device, dtype=f32)
+        nv.check(nv.load().lemas_text_embedding(C.byref(self._weights), nv.ptr(ids), nv.ptr(drop), nv.ptr(out), B, N,
+                                                nv.ptr(self._ws), self._ws.numel(), nv.stream()))
+        return out

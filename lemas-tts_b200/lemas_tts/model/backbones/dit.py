@@ -5,8 +5,9 @@ The module tree only carries parameters under the reference's state-dict keys.  
 weights are packed for the native engine (lemas_tts.engine.DiTEngine) and every DiT FLOP — input projection,
 conv position embedding, 22 AdaLN-zero blocks, final norm and projection — runs in the sm_100a kernels.
 
-The text embedding (dit.py:51-81: embedding + abs-pos + ConvNeXtV2/GRN blocks) runs twice per `sample()`, not per
-ODE step; it is host-level tensor plumbing in fp32 torch ops on the same device (kernelise next).
+The text embedding (dit.py:51-81: embedding + abs-pos + ConvNeXtV2/GRN blocks) runs once per `sample()` for the
+conditional and unconditional copies of the text; on the device it is `lemas_text_embedding` (csrc/text.cu).  The
+torch statement of the same arithmetic in `TextEmbedding.forward` is what the CPU tests compare with the oracle.
 """
 from __future__ import annotations
 
@@ -54,8 +55,28 @@ class TextEmbedding(nn.Module):
         """Conditional and unconditional embeddings in ONE batched pass (rows [0,B) keep their ids, rows [B,2B) have
         them dropped): every op of the block stack is per-sample, so this equals two separate calls."""
         B = text.shape[0]
+        if text.is_cuda:  # product path: liblemas_b200.so (csrc/text.cu); the torch code below is the CPU reference
+            ids = (torch.cat((text, text), 0) + 1)[:, :seq_len]
+            ids = F.pad(ids, (0, seq_len - ids.shape[1]), value=0)
+            drop = torch.zeros(2 * B, dtype=torch.uint8, device=text.device)
+            drop[B:] = 1
+            both = self.native().embed(ids, drop)
+            return both[:B], both[B:]
         both = self.forward(torch.cat((text, text), 0), seq_len, drop_rows=B)
         return both[:B].contiguous(), both[B:].contiguous()
+
+    def native(self):
+        """Weights packed for lemas_text_embedding (once per weight version / device)."""
+        w = self.text_embed.weight
+        key = (str(w.device), w._version, w.data_ptr())
+        if getattr(self, "_native", None) is None or self._native_key != key:
+            from ...engine import TextEngine
+
+            self._native = TextEngine(dict(self.state_dict()), text_dim=w.shape[1],
+                                      conv_layers=len(self.text_blocks) if self.extra_modeling else 0,
+                                      mask_padding=self.mask_padding, device=w.device, prefix="")
+            self._native_key = key
+        return self._native
 
     def forward(self, text: torch.Tensor, seq_len: int, drop_text: bool = False, drop_rows: int | None = None) -> torch.Tensor:
         text = (text + 1)[:, :seq_len]

@@ -109,3 +109,29 @@ def test_istft_matches_torch(B, T):
     assert got.shape == ref.shape
     scale = ref.abs().max().item()
     assert (got - ref).abs().max().item() < 2e-5 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("arch_name,B,N,lens", [("TINY_ARCH", 3, 131, [40, 22, 35]), ("FULL_ARCH", 2, 300, [150, 97]),
+                                                 ("FULL_ARCH", 1, 70, [90])])
+def test_text_embedding_matches_oracle(arch_name, B, N, lens):
+    """csrc/text.cu (gather + ConvNeXt-V2 / GRN blocks on the tcgen05 GEMMs) vs the CPU oracle, both CFG variants.
+    fp16 GEMM operands: |err| <= 2e-2 on outputs of magnitude O(1-10)."""
+    from lemas_tts import synthetic as syn
+    from lemas_tts.model.backbones.dit import DiT
+    from oracle import lemas_oracle as orc
+
+    arch = getattr(syn, arch_name)
+    sd = syn.make_dit_state_dict(arch, seed=11)
+    dit = DiT(**arch.to_kwargs())
+    dit.load_state_dict({k[len("transformer."):]: v for k, v in sd.items() if k.startswith("transformer.")}, strict=True)
+    dit = dit.cuda()
+    text = syn.synthetic_text_ids(B, max(lens), arch.text_num_embeds, seed=2, lengths=lens)
+    tc, tu = dit.text_embed.forward_pair(text.cuda(), N)
+    torch.cuda.synchronize()
+    for got, drop in ((tc, False), (tu, True)):
+        want = orc.text_embedding(sd, arch, text, N, drop_text=drop)
+        err = (got.cpu() - want).abs().max().item()
+        scale = want.abs().max().item()
+        assert err <= 2e-2 * max(1.0, scale / 4), f"drop={drop}: max err {err:.3e} (scale {scale:.2f})"
+        filler = (torch.nn.functional.pad((text + 1)[:, :N], (0, max(0, N - text.shape[1]))) == 0)
+        assert (got.cpu()[filler] == 0).all(), "filler rows must be exactly zero"
