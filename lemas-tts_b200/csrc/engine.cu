@@ -84,7 +84,7 @@ struct lemas_engine {
   // One captured ODE step per (shape, workspace) — replayed `steps` times; everything step-dependent is read from
   // device memory (step_begin_kernel), so the same executable graph serves every step and every later call.
   struct StepGraph {
-    int batch, seq, variants, has_kv, has_traj;
+    int batch, seq, steps, variants, has_kv;   // steps: the workspace carve-up (hence every captured pointer) depends on it
     float cfg;
     const void *ws, *rope, *traj;
     cudaGraphExec_t exec;
@@ -350,7 +350,8 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   LEMAS_CUDA_OK(cudaMemcpyAsync(b.y_state, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
   lemas_engine::StepGraph* g = nullptr;
   for (auto& cand : e->graphs)
-    if (cand.batch == a->batch && cand.seq == a->seq && cand.variants == variants && cand.has_kv == (kv2 != nullptr) &&
+    if (cand.batch == a->batch && cand.seq == a->seq && cand.steps == a->steps && cand.variants == variants &&
+        cand.has_kv == (kv2 != nullptr) &&
         cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope)
       g = &cand;
   int first_replayed = 0;
@@ -376,8 +377,8 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
       cudaGraphExecDestroy(e->graphs.front().exec);
       e->graphs.erase(e->graphs.begin());
     }
-    e->graphs.push_back({a->batch, a->seq, variants, kv2 != nullptr, a->trajectory != nullptr, a->cfg_strength,
-                         a->workspace, a->rope, a->trajectory, exec, nodes});
+    e->graphs.push_back({a->batch, a->seq, a->steps, variants, kv2 != nullptr, a->cfg_strength, a->workspace, a->rope,
+                         a->trajectory, exec, nodes});
     g = &e->graphs.back();
   }
   for (int i = first_replayed; i < a->steps; ++i) {

@@ -174,3 +174,19 @@ def test_prosody_path_from_raw_audio_matches_reference_golden(tmp_path):
                                  use_prosody_encoder=True)
         _check(out.cpu()[valid], gold[f"out_grl{int(grl)}"][valid], f"prosody grl={grl} out")
         _check(traj[-1].cpu()[valid], gold[f"last_grl{int(grl)}"][valid], f"prosody grl={grl} final state")
+
+
+def test_graph_cache_is_keyed_by_step_count():
+    """The workspace carve-up depends on the step count; a cached step graph must not be reused across step counts
+    (same shape, same workspace address)."""
+    case = gc.CASES["sample_tiny_b1"]
+    inp = gc.inputs(case)
+    model = _model(case["arch"], case["wseed"])
+    kw = dict(cond=inp["cond"].cuda(), text=inp["text"].cuda(), duration=inp["duration"], cfg_strength=2.0,
+              sway_sampling_coef=3.0, use_acc_grl=False, seed=99)
+    model.sample(**kw, steps=16, return_trajectory=False)            # grows the workspace, caches a 16-step graph
+    g5, _ = model.sample(**kw, steps=5, return_trajectory=False)     # graph path, same workspace address
+    e5, _ = model.sample(**kw, steps=5, return_trajectory=True)      # eager path
+    g16, _ = model.sample(**kw, steps=16, return_trajectory=False)
+    e16, _ = model.sample(**kw, steps=16, return_trajectory=True)
+    assert torch.equal(g5, e5) and torch.equal(g16, e16)
