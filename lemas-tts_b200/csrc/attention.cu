@@ -380,11 +380,8 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
     uint32_t box[3] = {64, ATT_D, 1};
     LEMAS_TRY(make_tensor_map_f16(&tmVT, vt, 3, dims, strides, box));
   }
-  static bool configured = false;
-  if (!configured) {
-    LEMAS_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  LEMAS_CUDA_OK(ensure_dynamic_smem(attention_kernel, ATT_SMEM, configured));
   AttnParams p;
   p.trace = g_att_trace;
   p.kv_len = kv_len;

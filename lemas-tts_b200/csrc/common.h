@@ -49,6 +49,19 @@ int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const uint
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remember it per (kernel instantiation, device), so a
+// process that drives several GPUs configures each of them.  `done` is a function-local static bitmask of the caller.
+template <class K>
+inline cudaError_t ensure_dynamic_smem(K kernel, int bytes, unsigned long long& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 64 && ((done >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev < 64) done |= 1ull << dev;
+  return e;
+}
+
 // LEMAS_PDL=0 disables programmatic dependent launch (A/B measurements)
 bool pdl_enabled();
 

@@ -414,11 +414,8 @@ int lemas_skinny_linear_f32(const float* x, const float* w, const float* b, floa
   LEMAS_REQUIRE(k % 128 == 0 && k <= 1536, "lemas_skinny_linear_f32: k must be a multiple of 128, <= 1536");
   LEMAS_REQUIRE(m >= 1, "lemas_skinny_linear_f32: m >= 1");
   const size_t smem = (size_t)32 * k * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    LEMAS_CUDA_OK(cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1536 * 4));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  LEMAS_CUDA_OK(ensure_dynamic_smem(skinny_linear_kernel, 32 * 1536 * 4, configured));
   int grid = sm_count();
   const int warps_needed = (n + 1) / 2;
   if (grid * 8 > warps_needed) grid = (warps_needed + 7) / 8;

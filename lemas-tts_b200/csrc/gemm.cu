@@ -293,12 +293,9 @@ template <int BLOCK_N, int EPI>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas,
                   cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = gemm_kernel<BLOCK_N, EPI>;
-  if (!configured) {
-    LEMAS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    configured = true;
-  }
+  LEMAS_CUDA_OK(ensure_dynamic_smem(kern, S::TOTAL, configured));
   const int m_tiles = p.batches * ((p.rows + BLOCK_M - 1) / BLOCK_M);
   const int n_tiles = (p.n + BLOCK_N - 1) / BLOCK_N;
   int grid = m_tiles * n_tiles;

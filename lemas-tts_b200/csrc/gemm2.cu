@@ -337,12 +337,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
 template <int EPI>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured = 0;
   auto kern = gemm2_kernel<EPI>;
-  if (!configured) {
-    LEMAS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
-    configured = true;
-  }
+  LEMAS_CUDA_OK(ensure_dynamic_smem(kern, G2_SMEM, configured));
   const int tiles = p.batches * ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
   int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
   if (pairs < 1) pairs = 1;

@@ -122,13 +122,22 @@ class CFM(nn.Module):
 
         from .backbones.prosody_encoder import extract_fbank_16k
 
-        embeds = []
         src_sr = self.mel_spec.target_sample_rate
+        fbanks = []
         for b in range(raw_audio.shape[0]):
             audio_b = raw_audio[b].unsqueeze(0)
             audio_16k = (torchaudio.functional.resample(audio_b, src_sr, 16_000) if src_sr != 16_000 else audio_b)
-            fbank = extract_fbank_16k(audio_16k.squeeze(0)).unsqueeze(0).to(device=device, dtype=torch.float32)
-            embeds.append(self.prosody_encoder(fbank, padding_mask=None)[0])
+            fbanks.append(extract_fbank_16k(audio_16k.squeeze(0)).to(device=device, dtype=torch.float32))
+        # The reference encodes one utterance at a time (no padding mask).  Every op of the encoder is per-sample, so
+        # utterances whose fbank has the same number of frames are encoded in one batched pass with the same result.
+        embeds = [None] * len(fbanks)
+        groups: dict = {}
+        for i, f in enumerate(fbanks):
+            groups.setdefault(f.shape[0], []).append(i)
+        for idx in groups.values():
+            emb = self.prosody_encoder(torch.stack([fbanks[i] for i in idx], dim=0), padding_mask=None)
+            for k, i in enumerate(idx):
+                embeds[i] = emb[k]
         return torch.stack(embeds, dim=0)
 
     @torch.no_grad()
