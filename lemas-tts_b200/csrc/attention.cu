@@ -71,6 +71,24 @@ DEVI float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of arithmetic.  The softmax warps are
+// issue-limited, so the scale-and-subtract and the row sum are done on register pairs.
+DEVI uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+DEVI void f32x2_split(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DEVI uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+DEVI uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
@@ -90,6 +108,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef LEMAS_ATT_TRACE  // per-CTA record after the warp stamps: [cta][8] = smid, globaltimer at entry / loop / merge / exit
+  long long* cta_rec = p.trace ? p.trace + 8 * 32 * 8 +
+      8 * ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  auto gtime = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  if (cta_rec && threadIdx.x == 64) {
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cta_rec[0] = smid; cta_rec[1] = gtime();
+  }
+#endif
   const int q0 = blockIdx.x * ATT_BM;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -213,6 +240,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     // Warps whose 32 query rows all lie beyond the sequence (last query tile) keep the barrier protocol going but do
     // no softmax work: their P rows only feed output rows that are never stored.
     const bool rows_dead = q0 + sub * 32 >= p.seq;
+#ifdef LEMAS_ATT_TRACE
+    if (cta_rec && threadIdx.x == 64) cta_rec[2] = gtime();
+#endif
     for (int j = 0; j < n_blocks; ++j) {
       if (rows_dead) {
         mbar_wait_lean(a_sfull, j & 1);
@@ -222,14 +252,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       }
       const int valid = min(max(kvl - j * ATT_BN - half * 64, 0), 64);  // keys of this half-block that exist
 #ifdef LEMAS_ATT_TRACE  // clock64 stamps of one CTA (tools/trace_att.py); costs ~8 % of the kernel, off by default
-      const bool tr = p.trace != nullptr && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 32;
+      // traced CTA = linear id stored in the unused stamp slot [warp 0][block 0][7]
+      const bool tr = p.trace != nullptr && lane == 0 && j < 32 &&
+                      (long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x == p.trace[7];
       long long* tp = p.trace + ((warp - 2) * 32 + j) * 8;
 #define ATT_STAMP(i) do { if (tr) tp[i] = clock64(); } while (0)
 #else
 #define ATT_STAMP(i) do { } while (0)
 #endif
       ATT_STAMP(0);
-      mbar_wait_lean(a_sfull, j & 1);
+      if (j == 0) mbar_wait_lean(a_sfull, 0);  // later blocks: S_j was awaited before P_{j-1} was stored (below)
       ATT_STAMP(1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
@@ -241,9 +273,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       ATT_STAMP(2);
 
       float mx = -INFINITY;
-      if (valid == 64) {
+      if (valid == 64) {  // four independent FMNMX3 chains of depth 8 instead of one of depth 32
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmax3f(mx, __uint_as_float(s0[i]), __uint_as_float(s1[i]));
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], __uint_as_float(s0[i]), __uint_as_float(s1[i]));
+        mx = fmaxf(fmax3f(m4[0], m4[1], m4[2]), m4[3]);
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -280,8 +314,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 
       // exp2 of the whole half-row into packed fp16 registers first; only then wait for the P buffer (free once
       // P V_{j-1} has read it) — waiting before the exponentials re-synchronised the four warps of a half every block
-      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      // Per key pair: one FFMA2 (scale, subtract the reference max), two MUFU.EX2, one FADD2 into one of four
+      // independent packed row-sum accumulators, one F2FP pack.
+      uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};   // bit pattern of (0.f, 0.f)
       uint32_t pk[32];
+      const uint64_t c2 = f32x2(c, c), nmc2 = f32x2(-mc, -mc);
       auto exp_block = [&](auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;  // full half-block: no per-element masking code at all
 #pragma unroll
@@ -291,16 +328,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
             pk[i] = 0u;
             continue;
           }
-          float e0 = ex2f(fmaf(__uint_as_float(col < 32 ? s0[col & 31] : s1[col & 31]), c, -mc));
-          float e1 = ex2f(fmaf(__uint_as_float(col + 1 < 32 ? s0[(col + 1) & 31] : s1[(col + 1) & 31]), c, -mc));
+          float x0, x1;
+          f32x2_split(ffma2(f32x2(__uint_as_float(col < 32 ? s0[col & 31] : s1[col & 31]),
+                                  __uint_as_float(col + 1 < 32 ? s0[(col + 1) & 31] : s1[(col + 1) & 31])),
+                            c2, nmc2), x0, x1);
+          const float e0 = ex2f(x0);
+          float e1 = ex2f(x1);
           if (!kFull && col + 1 >= valid) e1 = 0.f;
-          rs4[i & 3] += e0 + e1;
+          rs2[i & 3] = fadd2(rs2[i & 3], f32x2(e0, e1));
           pk[i] = pack_half2(e0, e1);
         }
       };
       if (valid == 64) exp_block(std::true_type{}); else exp_block(std::false_type{});
+      float rs4[4];
+      {
+        float lo, hi;
+        const uint64_t t01 = fadd2(rs2[0], rs2[1]), t23 = fadd2(rs2[2], rs2[3]);
+        f32x2_split(t01, lo, hi);
+        rs4[0] = lo; rs4[1] = hi;
+        f32x2_split(t23, lo, hi);
+        rs4[2] = lo; rs4[3] = hi;
+      }
       ATT_STAMP(4);
-      if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);
+      // The P buffer is free once P V_{j-1} has retired.  The MMA warp issues S_{j+1} after P V_{j-1} and commits it
+      // to s_full, and a commit tracks every MMA issued before it — so ONE wait on s_full(j+1) covers both "P is
+      // free" and "S_{j+1} is ready" (a successful mbarrier wait costs ~120 clk of pure latency in this loop).
+      if (j + 1 < n_blocks) mbar_wait_lean(a_sfull, (j + 1) & 1);
+      else if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);
       ATT_STAMP(5);
 #pragma unroll
       for (int u = 0; u < 8; ++u)  // 16-byte units of the 128-byte (64 keys x fp16) swizzled row
@@ -313,6 +367,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     }
 
     // ---- merge the two key halves and normalise
+#ifdef LEMAS_ATT_TRACE
+    if (cta_rec && threadIdx.x == 64) cta_rec[3] = gtime();
+#endif
     mbar_wait_lean(sb + ATT_OFF_BAR + 13 * 8, (n_blocks - 1) & 1);
     mbar_wait_lean(sb + ATT_OFF_BAR + 14 * 8, (n_blocks - 1) & 1);
     tc_fence_after();
@@ -351,6 +408,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem_base);
+#ifdef LEMAS_ATT_TRACE
+  if (cta_rec && threadIdx.x == 64) cta_rec[4] = gtime();
+#endif
 }
 
 }  // namespace lemas
