@@ -2,28 +2,33 @@
 //
 //   O = softmax(Q K^T / 8 + keymask) V        modules.py:483-491 (F.scaled_dot_product_attention call site)
 //
-// What bounds this kernel on B200: with head_dim 64 a 128 x 128 score block costs 512 tensor-core clocks (QK^T + PV)
-// but 16 384 exponentials, and the SFU delivers 16 exp2 / clk / SM (measured, profiles/r01b_mufu_exp2_throughput.log;
-// the packed f16x2 / bf16x2 forms are split into two MUFU ops and gain nothing) = 1024 clocks.  The design goal is
-// therefore to keep the SFU saturated: many independent softmax warps, no per-block work besides max / exp / sum / pack.
+// What bounds this kernel on B200 (measured, tools/trace_att.py + tools/micro/softmax_block_bench.cu):
+//  * SFU: a 128 x 128 score block costs 512 tensor-core clocks (QK^T + PV) but 16 384 exponentials at 16 exp2 / clk /
+//    SM = 1024 clocks (the packed f16x2 / bf16x2 forms are split into two MUFU ops and gain nothing);
+//  * shared-memory bandwidth (128 B / clk / SM): every tcgen05.mma streams its operands from shared memory.  With P
+//    staged through shared memory (generic stores + an SS-form P V) a block moved 144 KB = 1150 clk per CTA, more than
+//    the SFU needs.  P therefore never touches shared memory here: the softmax warps write it back INTO the TMEM
+//    columns its scores came from (fp16 pairs, 32 columns per 64 keys) and P V reads its A operand from TMEM
+//    (tcgen05.mma ... [d], [a_tmem], b_desc) — 96 KB per block, no proxy fence, no P buffer to wait for.
 //
 // One CTA = 128 query rows of one (batch, head); two CTAs are co-resident per SM.  Roles (320 threads):
 //   warp 0    TMA producer : Q tile once, then K tile [128 keys x 64] and V^T tile [64 x 128 keys] per KV block
-//                            into two 2-slot rings (128B swizzle, mbarrier tx-count); K slots recycle after S = Q K^T,
-//                            V slots after P V, so K runs a block further ahead
-//   warp 1    MMA issuer   : S = Q K^T (M128 N128 K16 x4) into TMEM cols [0,128); S for block j+1 is issued while the
-//                            softmax of block j runs.  P V is issued as TWO independent streams, one per 64-key half
-//                            of the block: O_A += P[:, 0:64] V[0:64], O_B += P[:, 64:128] V[64:128] (M128 N64 K16 x4
-//                            each), accumulated IN TMEM across all KV blocks (cols [128,192) and [192,256)).
+//                            into two 3-slot rings (128B swizzle, mbarrier tx-count)
+//   warp 1    MMA issuer   : every KV block is handled as two independent 64-key halves x = A, B, each with its own
+//                            TMEM columns, barriers and online-softmax state (intra-CTA split-KV):
+//                              S_x = Q K_x^T            (M128 N64 K16 x4, SS)   -> TMEM cols [64x, 64x+64)
+//                              O_x += P_x V_x           (M128 N64 K16 x4, TS)   -> TMEM cols [128+64x, 192+64x)
+//                            P_x(j) overwrites S_x(j) in place, so S_x(j+1) is issued right behind P_x(j) V_x(j) (the
+//                            tensor core executes one thread's MMAs in order).  The two halves never wait for each
+//                            other; half B is started half a block period after half A so that the two warps sharing
+//                            an SM sub-partition are not in their exponential phase at the same time.
 //   warps 2-9 softmax      : warps 2-5 own key half A, warps 6-9 key half B; thread == query row (tcgen05.ld 32x32b
-//                            gives each lane one row).  Each half runs its own online softmax (own running max and
-//                            row sum) over its 64 keys of every block — intra-CTA split-KV — so the two warps that
-//                            share a row never synchronise inside the loop; the halves are merged once at the end:
+//                            gives each lane one row).  Per block: wait S_x, read 64 scores, max, exp2 (packed
+//                            FFMA2 / FADD2 arithmetic), fp16 pack, tcgen05.st, arrive.  The accumulators are rescaled
+//                            lazily: O_x and l_x keep the scale of a reference max that is only advanced when a
+//                            block's max exceeds it by more than 2^8 (P then stays <= 256); after the first blocks
+//                            this almost never fires.  The halves are merged once at the end:
 //                            O = (w_A O_A + w_B O_B) / (w_A l_A + w_B l_B),  w_X = 2^((m_X - max(m_A, m_B)) c).
-//                            The accumulators are rescaled lazily: O_X and l_X keep the scale of a reference max that
-//                            is only advanced when a block's max exceeds it by more than 2^8 (P then stays <= 256,
-//                            exact in fp16 terms); after the first blocks this almost never fires, so the steady
-//                            state per block is: one TMEM read of S, max, exp2, sum, fp16 pack, swizzled smem store.
 // Fully masked KV blocks (keys >= kv_len) are skipped; the partial block is masked to zero probability.
 // K comes from the fused QKV buffer [b*seq, ld_qk]; V is read from the transposed copy [b, head, 64, vt_ld] that
 // the QKV GEMM epilogue writes, so both MMAs use K-major operands.
@@ -38,24 +43,29 @@ constexpr int ATT_THREADS = 320;
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BN = 128;   // keys per KV block
 constexpr int ATT_D = 64;
-constexpr int ATT_STAGES = 2;
+constexpr int ATT_STAGES = 3;
 
 constexpr int ATT_Q_BYTES = ATT_BM * ATT_D * 2;          // 16 KB
-constexpr int ATT_K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB
+constexpr int ATT_K_BYTES = ATT_BN * ATT_D * 2;          // 16 KB (two 8 KB halves of 64 keys)
 constexpr int ATT_V_BYTES = ATT_D * ATT_BN * 2;          // 16 KB (two 8 KB halves of 64 keys)
-constexpr int ATT_P_BYTES = ATT_BM * ATT_BN * 2;         // 32 KB (two 16 KB halves of 64 keys)
 constexpr int ATT_KV_STAGE = ATT_K_BYTES + ATT_V_BYTES;
 constexpr int ATT_OFF_KV = ATT_Q_BYTES;
-constexpr int ATT_OFF_P = ATT_OFF_KV + ATT_STAGES * ATT_KV_STAGE;
-constexpr int ATT_OFF_XCH = ATT_OFF_P;                   // float2 [2 halves][128 rows] (reference max, row sum):
-                                                         // reuses the P buffer after the last P V has retired
-constexpr int ATT_OFF_BAR = ATT_OFF_P + ATT_P_BYTES;
-constexpr int ATT_SMEM = ATT_OFF_BAR + 128;              // 112.1 KB: two CTAs per SM
+constexpr int ATT_OFF_XCH = ATT_OFF_KV;                  // float2 [2 halves][128 rows] (reference max, row sum):
+                                                         // reuses ring slot 0 after the last MMA has retired
+constexpr int ATT_OFF_BAR = ATT_OFF_KV + ATT_STAGES * ATT_KV_STAGE;
+constexpr int ATT_SMEM = ATT_OFF_BAR + 256;              // 112.25 KB: two CTAs per SM
+
+// barrier slots (8 bytes each) from ATT_OFF_BAR
+constexpr int BAR_Q = 0, BAR_KF = 1, BAR_KE = 4, BAR_VF = 7, BAR_VE = 10, BAR_SF = 13, BAR_PF = 15, BAR_OF = 17,
+              BAR_COUNT = 19;
 
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // advance the reference max only past 2^8 growth
+#ifndef ATT_DEPHASE_CLK
+#define ATT_DEPHASE_CLK 1000              // head start of key half A over key half B (about half a block period)
+#endif
 
 struct AttnParams {
-  long long* trace;   // debug: clock64 stamps of CTA (1,0,0) [warp][block][8]; nullptr in production
+  long long* trace;   // debug: clock64 stamps (tools/trace_att.py); nullptr in production
   const int* kv_len;
   __half* out;
   int seq, heads, inner;
@@ -71,8 +81,7 @@ DEVI float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of arithmetic.  The softmax warps are
-// issue-limited, so the scale-and-subtract and the row sum are done on register pairs.
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of arithmetic.
 DEVI uint64_t f32x2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -89,22 +98,70 @@ DEVI uint64_t fadd2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x (K/2) columns of packed fp16 pairs (row-major along K).
+DEVI void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#ifdef LEMAS_ATT_DEBUG  // hang hunting: every wait has a deadline; a waiter that misses it records who it is in
+                        // (pinned host) memory at p.trace and traps.  tools/att_hang_probe.py --debug
+DEVI void dbg_wait(long long* dbg, uint32_t bar_addr, uint32_t parity, int tag, int j) {
+  bool done = false;
+  for (int outer = 0; outer < 200000 && !done; ++outer) {   // same tight polling as the production waits
+#pragma unroll 1
+    for (int inner = 0; inner < 64; ++inner) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+      if (ok) { done = true; break; }
+    }
+  }
+  if (done) return;
+  if ((threadIdx.x & 31) == 0 || tag < 8) {
+    const int slot = atomicAdd(reinterpret_cast<int*>(dbg), 1);
+    if (slot < 500) {
+      long long* r = dbg + 1 + slot * 4;
+      unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      r[0] = (long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      r[1] = threadIdx.x >> 5;
+      r[2] = tag * 1000 + j;
+      r[3] = smid;
+    }
+    __threadfence_system();
+  }
+  const long long t2 = clock64() + 4000000ll;
+  while (clock64() < t2) { }
+  __trap();
+}
+#define ATT_WAIT_P(barptr, parity, tag, j) dbg_wait(p.trace, smem_u32(barptr), parity, tag, j)
+#define ATT_WAIT_A(addr, parity, tag, j) dbg_wait(p.trace, addr, parity, tag, j)
+#else
+#define ATT_WAIT_P(barptr, parity, tag, j) mbar_wait(barptr, parity)
+#define ATT_WAIT_A(addr, parity, tag, j) mbar_wait_lean(addr, parity)
+#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
                  const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;                  // [2]  K and V^T travel through separate 2-slot rings: a K slot is
-  uint64_t* k_empty = bars + 3;                 // [2]  free as soon as S_j = Q K_j^T has retired, a V slot only after
-  uint64_t* v_full = bars + 5;                  // [2]  P V_j — so K_{j+2} streams in a whole block earlier than a
-  uint64_t* v_empty = bars + 7;                 // [2]  shared ring would allow and S_{j+1} is never late
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_empty = bars + 10;
-  uint64_t* p_full = bars + 11;                 // [2] per key half
-  uint64_t* o_full = bars + 13;                 // [2] per key half
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* q_full = bars + BAR_Q;
+  uint64_t* k_full = bars + BAR_KF;    // [3]  K and V^T travel through separate rings: a K slot is free as soon as
+  uint64_t* k_empty = bars + BAR_KE;   // [3]  both halves of S_j have retired, a V slot only after both halves of
+  uint64_t* v_full = bars + BAR_VF;    // [3]  P V_j
+  uint64_t* v_empty = bars + BAR_VE;   // [3]
+  uint64_t* s_full = bars + BAR_SF;    // [2] per key half: S_x(j) is in TMEM (and P_x(j-1) V_x(j-1) has retired)
+  uint64_t* p_full = bars + BAR_PF;    // [2] per key half: P_x(j) is in TMEM
+  uint64_t* o_full = bars + BAR_OF;    // [2] per key half: the last P V has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,81 +197,87 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       mbar_init(v_full + s, 1);
       mbar_init(v_empty + s, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 8);            // one arrival per softmax warp
     for (int x = 0; x < 2; ++x) {
+      mbar_init(s_full + x, 1);
       mbar_init(p_full + x, 4);         // one arrival per softmax warp of the half
       mbar_init(o_full + x, 1);
     }
     fence_barrier_init();
   }
+#ifdef ATT_ALLOC_AFTER_PDL
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+#endif
   if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifndef ATT_ALLOC_AFTER_PDL
   pdl_trigger();
   pdl_wait();  // prologue overlapped the previous kernel's tail; q/k/v are visible from here on
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_o = tmem_base + ATT_BN;   // + 64 * half
+#endif
+  const uint32_t tmem_s = tmem_base;            // + 64 * half : S_x (64 fp32 columns) / P_x (32 columns of fp16 pairs)
+  const uint32_t tmem_o = tmem_base + ATT_BN;   // + 64 * half : O_x
 
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ATT_Q_BYTES);
       tma_load_3d(smem, &tmQK, q_full, h * ATT_D, q0, b);
       for (int j = 0; j < n_blocks; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = ((j >> 1) & 1) ^ 1;
+        const int s = j % ATT_STAGES;
+        const uint32_t ph = ((j / ATT_STAGES) & 1) ^ 1;
         uint8_t* sk = smem + ATT_OFF_KV + s * ATT_KV_STAGE;
-        mbar_wait(k_empty + s, ph);
+        ATT_WAIT_P(k_empty + s, ph, 1, j);
         mbar_arrive_expect_tx(k_full + s, ATT_K_BYTES);
         tma_load_3d(sk, &tmQK, k_full + s, p.inner + h * ATT_D, j * ATT_BN, b);
-        mbar_wait(v_empty + s, ph);
+        ATT_WAIT_P(v_empty + s, ph, 2, j);
         mbar_arrive_expect_tx(v_full + s, ATT_V_BYTES);
         tma_load_3d(sk + ATT_K_BYTES, &tmVT, v_full + s, j * ATT_BN, 0, b * p.heads + h);
         tma_load_3d(sk + ATT_K_BYTES + ATT_V_BYTES / 2, &tmVT, v_full + s, j * ATT_BN + 64, 0, b * p.heads + h);
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc_s = umma_idesc_f16(ATT_BM, ATT_BN);
-    constexpr uint32_t idesc_o = umma_idesc_f16(ATT_BM, ATT_D);
+    constexpr uint32_t idesc = umma_idesc_f16(ATT_BM, 64);   // both MMA shapes are M128 N64 K16
     const uint32_t sq = smem_u32(smem);
-    const uint32_t sp = smem_u32(smem + ATT_OFF_P);
-    auto issue_s = [&](int j) {  // S = Q K_j^T
-      const uint32_t sk = smem_u32(smem + ATT_OFF_KV + (j & 1) * ATT_KV_STAGE);
+    auto issue_s = [&](int x, int j) {  // S_x(j) = Q K_j[64x : 64x+64]^T
+      const uint32_t sk = smem_u32(smem + ATT_OFF_KV + (j % ATT_STAGES) * ATT_KV_STAGE) + x * (ATT_K_BYTES / 2);
       const uint64_t adesc = umma_desc_sw128(sq), bdesc = umma_desc_sw128(sk);
 #pragma unroll
-      for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tmem_s, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-      umma_commit(s_full);
-      umma_commit(k_empty + (j & 1));
+      for (int k = 0; k < ATT_D / 16; ++k) umma_f16_ss(tmem_s + x * 64, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
+      umma_commit(s_full + x);
+      if (x == 1) umma_commit(k_empty + (j % ATT_STAGES));
     };
-    mbar_wait(q_full, 0);
-    mbar_wait(k_full + 0, 0);
+    ATT_WAIT_P(q_full, 0, 3, 0);
+    ATT_WAIT_P(k_full + 0, 0, 4, 0);
     tc_fence_after();
-    if (elect_one()) issue_s(0);
+    if (elect_one()) issue_s(0, 0);
+    __syncwarp();
+    if (ATT_DEPHASE_CLK > 0 && n_blocks > 2) {  // head start for key half A (see the header)
+      const long long t_go = clock64() + ATT_DEPHASE_CLK;
+      while (clock64() < t_go) { }
+    }
+    if (elect_one()) issue_s(1, 0);
     __syncwarp();
     for (int j = 0; j < n_blocks; ++j) {
-      if (j + 1 < n_blocks) {
-        mbar_wait(k_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
-        mbar_wait(s_empty, j & 1);  // every softmax thread has pulled its part of S_j out of TMEM
-        tc_fence_after();
-        if (elect_one()) issue_s(j + 1);
-        __syncwarp();
-      }
-      const uint32_t sv = smem_u32(smem + ATT_OFF_KV + (j & 1) * ATT_KV_STAGE + ATT_K_BYTES);
-      mbar_wait(v_full + (j & 1), (j >> 1) & 1);
+      const bool last = j + 1 == n_blocks;
+      const uint32_t sv = smem_u32(smem + ATT_OFF_KV + (j % ATT_STAGES) * ATT_KV_STAGE + ATT_K_BYTES);
+      ATT_WAIT_P(v_full + (j % ATT_STAGES), (j / ATT_STAGES) & 1, 5, j);
+      if (!last) ATT_WAIT_P(k_full + ((j + 1) % ATT_STAGES), ((j + 1) / ATT_STAGES) & 1, 4, j + 1);
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {  // O_x (+)= P_j[:, 64x : 64x+64] V_j[64x : 64x+64]
-        mbar_wait(p_full + x, j & 1);
+      for (int x = 0; x < 2; ++x) {
+        ATT_WAIT_P(p_full + x, j & 1, 6 + x, j);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t adesc = umma_desc_sw128(sp + x * (ATT_P_BYTES / 2));
+          // O_x (+)= P_x(j) V_j[64x : 64x+64]; A = P from TMEM: 8 columns (16 fp16) per K16 step
           const uint64_t bdesc = umma_desc_sw128(sv + x * (ATT_V_BYTES / 2));
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_o + x * ATT_D, adesc + 2 * ks, bdesc + 2 * ks, idesc_o, (j | ks) != 0 ? 1u : 0u);
-          umma_commit(o_full + x);
-          if (x == 1) umma_commit(v_empty + (j & 1));
+            umma_f16_ts(tmem_o + x * ATT_D, tmem_s + x * 64 + 8 * ks, bdesc + 2 * ks, idesc, (j | ks) != 0 ? 1u : 0u);
+          if (x == 1) umma_commit(v_empty + (j % ATT_STAGES));
+          if (last) umma_commit(o_full + x);
+          else issue_s(x, j + 1);       // overwrites P_x(j): executes behind the P V just issued
         }
         __syncwarp();
       }
@@ -227,31 +290,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
     float m_ref = -INFINITY;           // max the accumulators O_half / l are currently scaled by
     float l_run = 0.f;
-    // 32-bit shared-window addresses (one register each, immediates for the rest): the softmax loop is issue-bound,
-    // every instruction of address arithmetic or pointer conversion in it costs throughput
+    // 32-bit shared-window addresses (one register each): the softmax loop is latency-bound, every instruction of
+    // address arithmetic or pointer conversion in it costs throughput
     const uint32_t sb = smem_u32(smem);
-    const uint32_t a_sfull = sb + ATT_OFF_BAR + 9 * 8, a_sempty = sb + ATT_OFF_BAR + 10 * 8;
-    const uint32_t a_pfull = sb + ATT_OFF_BAR + (11 + half) * 8, a_ofull = sb + ATT_OFF_BAR + (13 + half) * 8;
-    const uint32_t a_prow = sb + ATT_OFF_P + half * (ATT_P_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128;
-    const uint32_t xor7 = (r & 7) << 4;
+    const uint32_t a_sfull = sb + ATT_OFF_BAR + (BAR_SF + half) * 8, a_pfull = sb + ATT_OFF_BAR + (BAR_PF + half) * 8;
     const uint32_t t_s = tmem_s + lane_addr + half * 64;
     const uint32_t t_o = tmem_o + lane_addr + half * ATT_D;
 
     // Warps whose 32 query rows all lie beyond the sequence (last query tile) keep the barrier protocol going but do
-    // no softmax work: their P rows only feed output rows that are never stored.
+    // no softmax work: their P rows (left as whatever S held) only feed output rows that are never stored.
     const bool rows_dead = q0 + sub * 32 >= p.seq;
 #ifdef LEMAS_ATT_TRACE
     if (cta_rec && threadIdx.x == 64) cta_rec[2] = gtime();
 #endif
     for (int j = 0; j < n_blocks; ++j) {
       if (rows_dead) {
-        mbar_wait_lean(a_sfull, j & 1);
-        if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);  // never run a p_full phase ahead of the live warps
-        if (lane == 0) { mbar_arrive_s(a_sempty); mbar_arrive_s(a_pfull); }
+        ATT_WAIT_A(a_sfull, j & 1, 12 + half, j);
+        // every lane polls on its own: without this reconvergence lane 0 (the only one that arrives) can run ahead,
+        // the barrier laps the other 31 lanes by two phases and their parity wait never succeeds
+        __syncwarp();
+        if (lane == 0) mbar_arrive_s(a_pfull);
         continue;
       }
       const int valid = min(max(kvl - j * ATT_BN - half * 64, 0), 64);  // keys of this half-block that exist
-#ifdef LEMAS_ATT_TRACE  // clock64 stamps of one CTA (tools/trace_att.py); costs ~8 % of the kernel, off by default
+#ifdef LEMAS_ATT_TRACE  // clock64 stamps of one CTA (tools/trace_att.py); costs a few % of the kernel, off by default
       // traced CTA = linear id stored in the unused stamp slot [warp 0][block 0][7]
       const bool tr = p.trace != nullptr && lane == 0 && j < 32 &&
                       (long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x == p.trace[7];
@@ -261,15 +323,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 #define ATT_STAMP(i) do { } while (0)
 #endif
       ATT_STAMP(0);
-      if (j == 0) mbar_wait_lean(a_sfull, 0);  // later blocks: S_j was awaited before P_{j-1} was stored (below)
+      ATT_WAIT_A(a_sfull, j & 1, 8 + half, j);   // S_x(j) landed; P_x(j-1) V_x(j-1) retired before it (same issuing thread)
       ATT_STAMP(1);
       tc_fence_after();
       uint32_t s0[32], s1[32];
       tmem_ld_32x32(t_s, s0);
       tmem_ld_32x32(t_s + 32, s1);
       tmem_ld_wait();
-      tc_fence_before();
-      if (lane == 0) mbar_arrive_s(a_sempty);  // S_j is in registers (tcgen05.wait::ld is warp-wide): S_{j+1} may land
       ATT_STAMP(2);
 
       float mx = -INFINITY;
@@ -292,9 +352,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         const float m_new = grow ? mx : m_ref;
         const float alpha = (m_ref == -INFINITY) ? 0.f : ex2f((m_ref - m_new) * c);
         l_run *= alpha;
-        if (j > 0) {  // O_half holds the sum of blocks < j: rescale it in TMEM once P V_{j-1} has retired
-          mbar_wait_lean(a_ofull, (j - 1) & 1);
-          tc_fence_after();
+        if (j > 0) {  // O_half holds the sum of blocks < j (retired, see the s_full wait): rescale it in TMEM
 #pragma unroll 1
           for (int cc = 0; cc < ATT_D; cc += 8) {  // narrow chunks: S_j (64 registers) stays live across this
             uint32_t v[8];
@@ -304,16 +362,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
             for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
             tmem_st_32x32_x8(t_o + cc, v);
           }
-          tmem_st_wait();
-          tc_fence_before();
         }
         m_ref = m_new;
       }
       const float mc = (m_ref == -INFINITY) ? 0.f : m_ref * c;
       ATT_STAMP(3);
 
-      // exp2 of the whole half-row into packed fp16 registers first; only then wait for the P buffer (free once
-      // P V_{j-1} has read it) — waiting before the exponentials re-synchronised the four warps of a half every block
       // Per key pair: one FFMA2 (scale, subtract the reference max), two MUFU.EX2, one FADD2 into one of four
       // independent packed row-sum accumulators, one F2FP pack.
       uint64_t rs2[4] = {0ull, 0ull, 0ull, 0ull};   // bit pattern of (0.f, 0.f)
@@ -340,27 +394,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         }
       };
       if (valid == 64) exp_block(std::true_type{}); else exp_block(std::false_type{});
-      float rs4[4];
-      {
-        float lo, hi;
-        const uint64_t t01 = fadd2(rs2[0], rs2[1]), t23 = fadd2(rs2[2], rs2[3]);
-        f32x2_split(t01, lo, hi);
-        rs4[0] = lo; rs4[1] = hi;
-        f32x2_split(t23, lo, hi);
-        rs4[2] = lo; rs4[3] = hi;
-      }
       ATT_STAMP(4);
-      // The P buffer is free once P V_{j-1} has retired.  The MMA warp issues S_{j+1} after P V_{j-1} and commits it
-      // to s_full, and a commit tracks every MMA issued before it — so ONE wait on s_full(j+1) covers both "P is
-      // free" and "S_{j+1} is ready" (a successful mbarrier wait costs ~120 clk of pure latency in this loop).
-      if (j + 1 < n_blocks) mbar_wait_lean(a_sfull, (j + 1) & 1);
-      else if (j > 0) mbar_wait_lean(a_ofull, (j - 1) & 1);
-      ATT_STAMP(5);
-#pragma unroll
-      for (int u = 0; u < 8; ++u)  // 16-byte units of the 128-byte (64 keys x fp16) swizzled row
-        sts128(a_prow + ((u << 4) ^ xor7), pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-      l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
-      fence_proxy_async_smem();  // make the generic-proxy P stores visible to the tensor core (async proxy)
+      // P_x(j) -> TMEM, over the first 32 of the 64 columns S_x(j) was read from: column k holds keys (2k, 2k+1)
+      tmem_st_32x32(t_s, pk);
+      {
+        float lo, hi, lo2, hi2;
+        f32x2_split(fadd2(rs2[0], rs2[1]), lo, hi);
+        f32x2_split(fadd2(rs2[2], rs2[3]), lo2, hi2);
+        l_run += (lo + hi) + (lo2 + hi2);
+      }
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_s(a_pfull);
       ATT_STAMP(6);
@@ -370,10 +414,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 #ifdef LEMAS_ATT_TRACE
     if (cta_rec && threadIdx.x == 64) cta_rec[3] = gtime();
 #endif
-    mbar_wait_lean(sb + ATT_OFF_BAR + 13 * 8, (n_blocks - 1) & 1);
-    mbar_wait_lean(sb + ATT_OFF_BAR + 14 * 8, (n_blocks - 1) & 1);
+    ATT_WAIT_A(sb + ATT_OFF_BAR + BAR_OF * 8, 0, 10, 0);
+    ATT_WAIT_A(sb + ATT_OFF_BAR + (BAR_OF + 1) * 8, 0, 11, 0);
     tc_fence_after();
-    float2* xch = reinterpret_cast<float2*>(smem + ATT_OFF_XCH);  // P buffer: free now that every P V has retired
+    float2* xch = reinterpret_cast<float2*>(smem + ATT_OFF_XCH);  // ring slot 0: free now that every MMA has retired
     xch[half * ATT_BM + r] = make_float2(m_ref, l_run);
     named_bar_sync(1 + sub, 64);  // the two warps that share these 32 rows
     const float2 other = xch[(half ^ 1) * ATT_BM + r];

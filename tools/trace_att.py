@@ -4,7 +4,7 @@ Builds a tracing variant of the library (attention.cu with -DLEMAS_ATT_TRACE) ne
     python tools/trace_att.py --build        # here (nvcc, no GPU) -> lemas-tts_b200/lib/liblemas_b200_trace.so
     python tools/trace_att.py [seq]          # on the GPU box: prints per-phase clocks per warp and the block period
 Stamps per KV block: 0 loop top, 1 S_j visible, 2 S_j in registers, 3 max / lazy rescale done, 4 exponentials done,
-5 P buffer free (P V_{j-1} retired), 6 P_j stored + arrive."""
+6 P_j stored to TMEM + arrive."""
 import ctypes
 import subprocess
 import sys
@@ -53,15 +53,16 @@ def main():
     rec = trace[8 * 32 * 8:].view(n_cta, 8).cpu()
     t = trace[:8 * 32 * 8].view(8, 32, 8).cpu()
     nb = min((seq + 127) // 128, 32)
-    names = ["wait S", "ld S", "max", "exp", "wait Pfree", "store P"]
+    names = ["wait S", "ld S", "max", "exp", "store P"]
     print(f"seq {seq}, traced CTA {target}: {nb} KV blocks; clocks per phase, mean over blocks 3..{nb - 2}")
     print("warp  half sub | " + " | ".join(f"{n:>10s}" for n in names) + " |   period")
     for w in range(8):
         tw = t[w, :nb]
-        d = (tw[:, 1:7] - tw[:, 0:6]).double()
+        st = tw[:, [0, 1, 2, 3, 4, 6]]          # stamp 5 is unused since P goes to TMEM
+        d = (st[:, 1:] - st[:, :-1]).double()
         per = (tw[1:, 0] - tw[:-1, 0]).double()
         sl = slice(3, nb - 1)
-        print(f"{w + 2:4d}  {w // 4:4d} {(w + 2) & 3:3d} | " + " | ".join(f"{d[sl, i].mean().item():10.0f}" for i in range(6))
+        print(f"{w + 2:4d}  {w // 4:4d} {(w + 2) & 3:3d} | " + " | ".join(f"{d[sl, i].mean().item():10.0f}" for i in range(5))
               + f" | {per[3:nb - 2].mean().item():8.0f}")
     t0 = t[:, 0, 0].min()
     print("first stamp -> last stamp (clk):", (t[:, nb - 1, 6].max() - t0).item())
