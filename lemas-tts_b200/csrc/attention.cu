@@ -60,6 +60,9 @@ constexpr int BAR_Q = 0, BAR_KF = 1, BAR_KE = 4, BAR_VF = 7, BAR_VE = 10, BAR_SF
               BAR_COUNT = 19;
 
 constexpr float ATT_RESCALE_LOG2 = 8.0f;  // advance the reference max only past 2^8 growth
+#ifndef ATT_POLY_EVERY
+#define ATT_POLY_EVERY 4                  // one key pair in 4 gets its exp2 from the FMA pipe (0 = all on the SFU)
+#endif
 #ifndef ATT_DEPHASE_CLK
 #define ATT_DEPHASE_CLK 1000              // head start of key half A over key half B (about half a block period)
 #endif
@@ -386,8 +389,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
           f32x2_split(ffma2(f32x2(__uint_as_float(col < 32 ? s0[col & 31] : s1[col & 31]),
                                   __uint_as_float(col + 1 < 32 ? s0[(col + 1) & 31] : s1[(col + 1) & 31])),
                             c2, nmc2), x0, x1);
-          const float e0 = ex2f(x0);
-          float e1 = ex2f(x1);
+          float e0, e1;
+          if (kFull && ATT_POLY_EVERY > 0 && (i % (ATT_POLY_EVERY > 0 ? ATT_POLY_EVERY : 1)) == 0) {
+            // exp2 on the FMA / ALU pipes for one key pair in ATT_POLY_EVERY (the SFU is the contended unit):
+            // x = n + f, n = round(x) via the 1.5 * 2^23 magic constant, f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+            // polynomial (max relative error 7.5e-5, below the fp16 rounding of P); 2^n added into the exponent field.
+            // x <= 8 by the lazy-rescale bound; the clamp keeps n inside the exponent range (result < 2^-125 ~ 0).
+            const uint64_t xc = f32x2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+            const uint64_t t2 = fadd2(xc, f32x2(12582912.f, 12582912.f));
+            const uint64_t f2 = ffma2(fadd2(t2, f32x2(-12582912.f, -12582912.f)), f32x2(-1.f, -1.f), xc);
+            uint64_t p2 = ffma2(f32x2(0.055171460f, 0.055171460f), f2, f32x2(0.24261086f, 0.24261086f));
+            p2 = ffma2(p2, f2, f32x2(0.69326097f, 0.69326097f));
+            p2 = ffma2(p2, f2, f32x2(0.99992812f, 0.99992812f));
+            float p0, p1, t0, t1;
+            f32x2_split(p2, p0, p1);
+            f32x2_split(t2, t0, t1);
+            e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+            e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+          } else {
+            e0 = ex2f(x0);
+            e1 = ex2f(x1);
+          }
           if (!kFull && col + 1 >= valid) e1 = 0.f;
           rs2[i & 3] = fadd2(rs2[i & 3], f32x2(e0, e1));
           pk[i] = pack_half2(e0, e1);
