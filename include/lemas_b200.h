@@ -139,6 +139,14 @@ int lemas_dwconv7_ln(const float* x, const float* dw_w, const float* dw_b, const
 int lemas_istft_1024(const float* head, int32_t ld_head, float* frames_ws, float* wav, int32_t batch, int32_t t,
                      void* stream);
 
+/* Mel front-end of the reference audio (MelSpec.forward / get_vocos_mel_spectrogram, modules.py:75-101,130-143):
+ * |STFT| (n_fft 1024, hop 256, periodic hann, center + reflect padding, power 1) -> mel filterbank -> log(clamp 1e-5).
+ * wav: fp32 [batch, wav_ld] (nw valid samples per row, nw > 512); fb: fp32 [513, n_mels] filterbank (HTK, norm=None:
+ * torchaudio.functional.melscale_fbanks layout); fb_range: int32 [n_mels, 2] = [first, last+1) non-zero bin of every
+ * filter; mel: fp32 [batch, n_mels, nw/256 + 1]. */
+int lemas_mel_spectrogram_1024(const float* wav, int32_t batch, int32_t nw, int32_t wav_ld, const float* fb,
+                               const int32_t* fb_range, int32_t n_mels, float* mel, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Engine-level entry points: the whole sampler / vocoder as a sequence of the launches above, driven from C++.
  * ---------------------------------------------------------------------------------------------------------- */

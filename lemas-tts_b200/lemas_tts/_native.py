@@ -104,6 +104,7 @@ SIGNATURES = {
     "lemas_cfg_euler": (C.c_int, [vp, i32, vp, vp, i32, i32, vp, i32, i32, f32, f32, f32, vp]),
     "lemas_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "lemas_istft_1024": (C.c_int, [vp, i32, vp, vp, i32, i32, vp]),
+    "lemas_mel_spectrogram_1024": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
     "lemas_engine_workspace_bytes": (i64, [C.POINTER(DitConfig), i32, i32, i32]),
     "lemas_engine_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(vp)]),
     "lemas_engine_destroy": (None, [vp]),

@@ -4,7 +4,8 @@ The reference's nn.Modules compute with stock PyTorch ops; here the modules belo
 reference's state-dict names so that `load_checkpoint` (strict) works unchanged — the arithmetic of the DiT blocks
 runs in liblemas_b200.so (csrc/*.cu), driven by lemas_tts.engine.  Their `forward` is deliberately absent.
 
-MelSpec (modules.py:75-143) stays torchaudio: once per utterance, host plumbing.
+MelSpec (modules.py:75-143): CUDA waveforms go through the native STFT + mel kernel (csrc/frontend.cu, SURVEY.md §8
+row a1); CPU waveforms (host-side data preparation, as in the reference) use torchaudio like the reference does.
 """
 from __future__ import annotations
 
@@ -27,6 +28,12 @@ _MEL_CACHE: dict = {}
 def get_vocos_mel_spectrogram(waveform, n_fft=1024, n_mel_channels=100, target_sample_rate=24000, hop_length=256,
                               win_length=1024):
     """modules.py:75-101: |STFT| (power 1, hann, center) -> HTK mel (no norm) -> log(clamp 1e-5)."""
+    if waveform.dim() == 3:
+        waveform = waveform.squeeze(1)
+    assert waveform.dim() == 2
+    if waveform.is_cuda and (n_fft, hop_length, win_length) == (1024, 256, 1024) and waveform.shape[-1] > 512:
+        from lemas_tts import ops
+        return ops.mel_spectrogram_1024(waveform.float().contiguous(), n_mel_channels, target_sample_rate)
     key = (str(waveform.device), n_fft, n_mel_channels, target_sample_rate, hop_length, win_length)
     tf = _MEL_CACHE.get(key)
     if tf is None:

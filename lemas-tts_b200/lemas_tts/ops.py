@@ -5,6 +5,8 @@ op-level parity tests and by the weight packer; the sampler itself is driven fro
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _native as nv
@@ -123,6 +125,46 @@ def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b):
     nv.check(nv.load().lemas_dwconv7_ln(nv.ptr(x), nv.ptr(dw_w), nv.ptr(dw_b), nv.ptr(ln_w), nv.ptr(ln_b), nv.ptr(out),
                                         b, t, dim, nv.stream()))
     return out
+
+
+_MEL_FB: dict = {}
+
+
+def mel_filterbank(n_mels: int = 100, sample_rate: int = 24000, n_fft: int = 1024):
+    """HTK mel filterbank [n_fft/2+1, n_mels], norm=None, f_min 0, f_max sr/2 — the matrix torchaudio's MelScale
+    holds for the reference's MelSpectrogram (modules.py:83-93) — plus the [first, last+1) non-zero bin of each filter."""
+    n_freqs = n_fft // 2 + 1
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + 0.0 / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + (sample_rate / 2.0) / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    fb = torch.max(torch.zeros(1), torch.min(down, up)).contiguous()
+    nz = fb > 0
+    first = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+    last = torch.where(nz.any(0), n_freqs - nz.flip(0).float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+    return fb, torch.stack((first, last), dim=1).to(torch.int32).contiguous()
+
+
+def mel_spectrogram_1024(wav: torch.Tensor, n_mels: int = 100, sample_rate: int = 24000) -> torch.Tensor:
+    """wav: fp32 [b, nw] on the GPU -> log-mel fp32 [b, n_mels, nw//256 + 1]   (modules.py:75-101, csrc/frontend.cu)."""
+    nv.require_device()
+    _chk(wav, f32, "wav")
+    assert wav.dim() == 2
+    key = (wav.device, n_mels, sample_rate)
+    if key not in _MEL_FB:
+        fb, rng = mel_filterbank(n_mels, sample_rate, 1024)
+        _MEL_FB[key] = (fb.to(wav.device), rng.to(wav.device))
+    fb, rng = _MEL_FB[key]
+    b, nw = wav.shape
+    mel = torch.empty(b, n_mels, nw // 256 + 1, device=wav.device, dtype=f32)
+    nv.check(nv.load().lemas_mel_spectrogram_1024(nv.ptr(wav), b, nw, wav.stride(0), nv.ptr(fb), nv.ptr(rng), n_mels,
+                                                  nv.ptr(mel), nv.stream()))
+    return mel
 
 
 def istft_1024(head: torch.Tensor, batch: int, t: int) -> torch.Tensor:

@@ -1,0 +1,61 @@
+"""GPU parity of the native mel front-end (csrc/frontend.cu) through the C ABI.
+
+Checkers: (1) the golden vector minted from the verbatim reference MelSpec (oracle/gen_golden.py, modules.py:75-143);
+(2) the CPU oracle (oracle.lemas_oracle.mel_spectrogram, fp32) on other lengths, including the C2 / C5 reference-audio
+sizes and lengths that are not multiples of the hop.  Tolerance: 2e-4 absolute on the log-mel (fp32 FFT vs torch's
+pocketfft; values span about [-11.5, 6]).
+"""
+import pytest
+import torch
+
+from lemas_tts import synthetic as syn
+from oracle import lemas_oracle as orc
+import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+
+
+def test_mel_matches_reference_golden():
+    from lemas_tts.model.modules import MelSpec
+
+    want = torch.load(gc.GOLDEN / "melspec.pt", weights_only=True)["mel"]
+    wav = syn.synthetic_ref_audio(2, 24000, seed=9).cuda()
+    got = MelSpec()(wav).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("batch,nw", [(1, 240000), (3, 5000), (2, 513), (1, 96001), (1, 720000)])
+def test_mel_matches_oracle(batch, nw):
+    from lemas_tts import ops
+
+    wav = syn.synthetic_ref_audio(batch, nw, seed=nw % 97)
+    want = orc.mel_spectrogram(wav)
+    got = ops.mel_spectrogram_1024(wav.cuda()).cpu()
+    assert got.shape == want.shape == (batch, 100, nw // 256 + 1)
+    assert (got - want).abs().max().item() < TOL
+
+
+def test_mel_rejects_short_audio():
+    from lemas_tts import ops
+
+    with pytest.raises(RuntimeError):
+        ops.mel_spectrogram_1024(torch.zeros(1, 512, device="cuda"))
+
+
+def test_mel_strided_batch_rows():
+    """wav_ld > nw: rows of a larger buffer (what CFM.sample passes for ragged raw-audio batches)."""
+    from lemas_tts import ops
+
+    big = syn.synthetic_ref_audio(2, 9000, seed=3)
+    view = big[:, :7000]
+    want = orc.mel_spectrogram(view.contiguous())
+    got = ops.mel_spectrogram_1024(view.cuda()).cpu() if view.cuda().is_contiguous() else None
+    wav = big.cuda()[:, :7000]
+    from lemas_tts import _native as nv
+    fb, rng = ops.mel_filterbank()
+    mel = torch.empty(2, 100, 7000 // 256 + 1, device="cuda")
+    nv.check(nv.load().lemas_mel_spectrogram_1024(wav.data_ptr(), 2, 7000, wav.stride(0), nv.ptr(fb.cuda()),
+                                                  nv.ptr(rng.cuda()), 100, nv.ptr(mel), nv.stream()))
+    assert (mel.cpu() - want).abs().max().item() < TOL
