@@ -33,7 +33,8 @@ int lemas_version(void);
 int lemas_device_supported(void);
 /* sizeof() of the ABI structs, for bindings to self-check their mirrors: 0 lemas_gemm_desc, 1 lemas_dit_config,
  * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights,
- * 7 lemas_text_block, 8 lemas_text_weights; else -1. */
+ * 7 lemas_text_block, 8 lemas_text_weights, 9 lemas_prosody_tdnn, 10 lemas_prosody_block, 11 lemas_prosody_weights;
+ * else -1. */
 int lemas_abi_sizeof(int which);
 /* Number of kernels this library has launched in the calling process since it was loaded (all entry points). */
 int64_t lemas_launch_count(void);
@@ -274,6 +275,53 @@ int64_t lemas_text_workspace_bytes(const lemas_text_weights* w, int32_t batch, i
  * out: fp32 [batch, seq, dim]. */
 int lemas_text_embedding(const lemas_text_weights* w, const int32_t* ids, const uint8_t* drop, float* out, int32_t batch,
                          int32_t seq, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Prosody path of the prosody-conditioned model, once per utterance (cfm.py:248-262): 24 kHz -> 16 kHz resampling,
+ * kaldi fbank, Pretssel ECAPA-TDNN (prosody_encoder.py:30-334).  fp32 throughout; activations channels-last.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lemas_prosody_tdnn {           /* TDNNBlock: Conv1d(same padding) -> ReLU -> LayerNorm(eps 1e-12)      */
+  const float* w;                             /* fp32 [k][cin/groups][cout]: nn.Conv1d weight permuted (2, 1, 0)      */
+  const float* b;                             /* fp32 [cout]                                                          */
+  const float* ln_w; const float* ln_b;       /* fp32 [cout]                                                          */
+  int32_t cin, cout, k, dil, groups;
+} lemas_prosody_tdnn;
+
+typedef struct lemas_prosody_block {          /* SERes2NetBlock (prosody_encoder.py:282-334), in == out channels      */
+  lemas_prosody_tdnn tdnn1;
+  lemas_prosody_tdnn res2[7];                 /* res2net_scale - 1 TDNNs on channels/scale channels each              */
+  lemas_prosody_tdnn tdnn2;
+  const float* se_w1; const float* se_b1;     /* fp32 [channels][se_channels] (transposed), [se_channels]             */
+  const float* se_w2; const float* se_b2;     /* fp32 [se_channels][channels] (transposed), [channels]                */
+} lemas_prosody_block;
+
+typedef struct lemas_prosody_weights {
+  int32_t input_dim, channels, n_blocks, scale, se_channels, att_channels, mfa_channels, embed_dim;
+  lemas_prosody_tdnn block0;                  /* encoder.blocks.0                                                      */
+  const lemas_prosody_block* blocks;          /* host array [n_blocks]: encoder.blocks.1 ..                            */
+  lemas_prosody_tdnn mfa;                     /* encoder.mfa                                                           */
+  lemas_prosody_tdnn asp_tdnn;                /* encoder.asp.tdnn (3*mfa_channels -> att_channels), tanh after         */
+  const float* asp_conv_w; const float* asp_conv_b;   /* fp32 [att_channels][mfa_channels] (transposed), [mfa_channels] */
+  const float* asp_norm_w; const float* asp_norm_b;   /* fp32 [2*mfa_channels]                                          */
+  const float* fc_w; const float* fc_b;               /* fp32 [2*mfa_channels][embed_dim] (transposed), [embed_dim]     */
+} lemas_prosody_weights;
+
+int64_t lemas_prosody_workspace_bytes(const lemas_prosody_weights* w, int32_t batch, int32_t t);
+/* ProsodyEncoder.forward(fbank, padding_mask=None) (prosody_encoder.py:421-432): fbank fp32 [batch, t, input_dim] ->
+ * L2-normalised embedding fp32 [batch, embed_dim]. */
+int lemas_prosody_encode(const lemas_prosody_weights* w, const float* fbank, int32_t batch, int32_t t, float* out,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* torchaudio.functional.resample (cfm.py:254) as a polyphase FIR: out[q*up + j] = sum_k taps[j][k] * xpad[q*down + k],
+ * xpad[p] = x[p - width].  taps: fp32 [up][n_taps] (host: sinc_interp_hann, lowpass width 6, rolloff 0.99). */
+int lemas_resample_sinc(const float* x, int32_t batch, int32_t n, int32_t x_ld, const float* taps, int32_t n_taps,
+                        int32_t width, int32_t up, int32_t down, float* y, int32_t n_out, int32_t y_ld, void* stream);
+
+/* extract_fbank_16k = torchaudio.compliance.kaldi.fbank(num_mel_bins, 16 kHz) (prosody_encoder.py:337-361):
+ * wav fp32 [batch, wav_ld] (n >= 400 valid samples) -> fp32 [batch, 1 + (n-400)/160, n_mels].
+ * window: fp32 [400] povey window; banks: fp32 [n_mels][257] kaldi mel banks; bank_range: int32 [n_mels][2]. */
+int lemas_kaldi_fbank_16k(const float* wav, int32_t batch, int32_t n, int32_t wav_ld, const float* window,
+                          const float* banks, const int32_t* bank_range, int32_t n_mels, float* out, void* stream);
 
 #ifdef __cplusplus
 }

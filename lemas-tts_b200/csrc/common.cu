@@ -106,6 +106,9 @@ int lemas_abi_sizeof(int which) {
     case 6: return (int)sizeof(lemas_vocos_weights);
     case 7: return (int)sizeof(lemas_text_block);
     case 8: return (int)sizeof(lemas_text_weights);
+    case 9: return (int)sizeof(lemas_prosody_tdnn);
+    case 10: return (int)sizeof(lemas_prosody_block);
+    case 11: return (int)sizeof(lemas_prosody_weights);
   }
   return -1;
 }

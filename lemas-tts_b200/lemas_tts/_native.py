@@ -84,6 +84,24 @@ class TextWeights(C.Structure):
                 ("blocks", C.POINTER(TextBlock))]
 
 
+class ProsodyTdnn(C.Structure):
+    _fields_ = [("w", vp), ("b", vp), ("ln_w", vp), ("ln_b", vp),
+                ("cin", i32), ("cout", i32), ("k", i32), ("dil", i32), ("groups", i32)]
+
+
+class ProsodyBlock(C.Structure):
+    _fields_ = [("tdnn1", ProsodyTdnn), ("res2", ProsodyTdnn * 7), ("tdnn2", ProsodyTdnn),
+                ("se_w1", vp), ("se_b1", vp), ("se_w2", vp), ("se_b2", vp)]
+
+
+class ProsodyWeights(C.Structure):
+    _fields_ = [("input_dim", i32), ("channels", i32), ("n_blocks", i32), ("scale", i32), ("se_channels", i32),
+                ("att_channels", i32), ("mfa_channels", i32), ("embed_dim", i32),
+                ("block0", ProsodyTdnn), ("blocks", C.POINTER(ProsodyBlock)), ("mfa", ProsodyTdnn),
+                ("asp_tdnn", ProsodyTdnn), ("asp_conv_w", vp), ("asp_conv_b", vp), ("asp_norm_w", vp),
+                ("asp_norm_b", vp), ("fc_w", vp), ("fc_b", vp)]
+
+
 # every symbol include/lemas_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "lemas_last_error": (C.c_char_p, []),
@@ -105,6 +123,10 @@ SIGNATURES = {
     "lemas_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "lemas_istft_1024": (C.c_int, [vp, i32, vp, vp, i32, i32, vp]),
     "lemas_mel_spectrogram_1024": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "lemas_prosody_workspace_bytes": (i64, [C.POINTER(ProsodyWeights), i32, i32]),
+    "lemas_prosody_encode": (C.c_int, [C.POINTER(ProsodyWeights), vp, i32, i32, vp, vp, i64, vp]),
+    "lemas_resample_sinc": (C.c_int, [vp, i32, i32, i32, vp, i32, i32, i32, i32, vp, i32, i32, vp]),
+    "lemas_kaldi_fbank_16k": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
     "lemas_engine_workspace_bytes": (i64, [C.POINTER(DitConfig), i32, i32, i32]),
     "lemas_engine_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(DitWeights), C.POINTER(vp)]),
     "lemas_engine_destroy": (None, [vp]),

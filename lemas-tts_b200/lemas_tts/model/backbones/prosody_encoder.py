@@ -1,9 +1,11 @@
 """Pretssel ECAPA-TDNN prosody encoder (reference lemas_tts/model/backbones/prosody_encoder.py:30-433).
 
 Runs ONCE per utterance, before the ODE loop (cfm.py:248-265): 16 kHz kaldi fbank (80 bins) -> ECAPA-TDNN ->
-L2-normalised 512-d embedding that conditions the mel (prosody_to_mel) and the text (prosody_text_proj).  It is
-host-level tensor plumbing in fp32 torch ops on the model's device (kernelise after the
-loop); parameter names follow the reference checkpoint (`prosody_encoder.encoder.*`) so released weights load.
+L2-normalised 512-d embedding that conditions the mel (prosody_to_mel) and the text (prosody_text_proj).  On the GPU
+the whole path runs in hand-written fp32 CUDA (csrc/prosody.cu through lemas_tts.prosody_native: polyphase resampler,
+kaldi fbank, ECAPA-TDNN); the nn.Modules below hold the parameters under the reference checkpoint's names
+(`prosody_encoder.encoder.*`, so released weights load) and keep the reference's torch arithmetic for CPU tensors and
+for the padding-mask variant the inference path never uses.
 """
 from __future__ import annotations
 
@@ -141,6 +143,13 @@ class ECAPA_TDNN(nn.Module):
         self.fc = nn.Conv1d(channels[-1] * 2, embed_dim, 1)
 
     def forward(self, x: Tensor, padding_mask: Optional[Tensor] = None) -> Tensor:
+        if x.is_cuda and padding_mask is None:
+            from lemas_tts import prosody_native
+            return prosody_native.ecapa_encode(self, x)
+        return self.forward_torch(x, padding_mask)
+
+    def forward_torch(self, x: Tensor, padding_mask: Optional[Tensor] = None) -> Tensor:
+        """The reference's arithmetic in torch ops (CPU tensors; checker of the native path in tests)."""
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):  # fp32 convolutions, like the CPU reference
             x = x.transpose(1, 2)
             feats = []
@@ -158,6 +167,9 @@ def extract_fbank_16k(audio_16k: Tensor) -> Tensor:
     tiled first (:337-361)."""
     if audio_16k.ndim == 1:
         audio_16k = audio_16k.unsqueeze(0)
+    if audio_16k.is_cuda:
+        from lemas_tts import prosody_native
+        return prosody_native.kaldi_fbank_80(audio_16k.float())[0]
     if audio_16k.shape[-1] < 400:
         audio_16k = audio_16k.repeat(1, 400 // audio_16k.shape[-1] + 1)
     return torchaudio.compliance.kaldi.fbank(audio_16k, num_mel_bins=80, sample_frequency=AUDIO_SAMPLE_RATE)

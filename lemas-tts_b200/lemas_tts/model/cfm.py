@@ -123,22 +123,20 @@ class CFM(nn.Module):
         from .backbones.prosody_encoder import extract_fbank_16k
 
         src_sr = self.mel_spec.target_sample_rate
+        raw_audio = raw_audio.to(device=device, dtype=torch.float32)
+        if raw_audio.is_cuda:
+            # The reference encodes one utterance at a time over the whole (padded) row raw_audio[b]; every stage is
+            # per-sample, so the rows of the batch go through the native kernels together with the same result:
+            # polyphase resampler -> kaldi fbank -> ECAPA-TDNN (csrc/prosody.cu).
+            from lemas_tts import prosody_native as pn
+            audio_16k = pn.resample(raw_audio.contiguous(), src_sr, 16_000)
+            return self.prosody_encoder(pn.kaldi_fbank_80(audio_16k), padding_mask=None)
         fbanks = []
         for b in range(raw_audio.shape[0]):
             audio_b = raw_audio[b].unsqueeze(0)
             audio_16k = (torchaudio.functional.resample(audio_b, src_sr, 16_000) if src_sr != 16_000 else audio_b)
             fbanks.append(extract_fbank_16k(audio_16k.squeeze(0)).to(device=device, dtype=torch.float32))
-        # The reference encodes one utterance at a time (no padding mask).  Every op of the encoder is per-sample, so
-        # utterances whose fbank has the same number of frames are encoded in one batched pass with the same result.
-        embeds = [None] * len(fbanks)
-        groups: dict = {}
-        for i, f in enumerate(fbanks):
-            groups.setdefault(f.shape[0], []).append(i)
-        for idx in groups.values():
-            emb = self.prosody_encoder(torch.stack([fbanks[i] for i in idx], dim=0), padding_mask=None)
-            for k, i in enumerate(idx):
-                embeds[i] = emb[k]
-        return torch.stack(embeds, dim=0)
+        return torch.stack([self.prosody_encoder(f.unsqueeze(0), padding_mask=None)[0] for f in fbanks], dim=0)
 
     @torch.no_grad()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None,

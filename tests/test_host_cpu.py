@@ -149,3 +149,50 @@ def test_text_embedding_pair_equals_two_passes():
     te = model.transformer.text_embed
     tc, tu = te.forward_pair(text, 131)
     assert torch.equal(tc, te(text, 131, drop_text=False)) and torch.equal(tu, te(text, 131, drop_text=True))
+
+
+def test_prosody_tables_match_torchaudio():
+    """The constant tables of the native prosody path (lemas_tts/prosody_native.py) against torchaudio's own:
+    resampling taps (cfm.py:254), povey window and kaldi mel banks (prosody_encoder.py:356-360)."""
+    import torchaudio
+    from torchaudio.compliance import kaldi
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+
+    from lemas_tts import prosody_native as pn
+
+    for orig, new in [(24000, 16000), (22050, 16000), (16000, 24000)]:
+        taps, width, up, down = pn.resample_taps(orig, new)
+        import math
+        g = math.gcd(orig, new)
+        want, w2 = _get_sinc_resample_kernel(orig, new, g, dtype=torch.float32)
+        assert width == w2 and (up, down) == (new // g, orig // g)
+        assert torch.equal(taps, want[:, 0, :])
+    # the polyphase form the kernel evaluates == torchaudio.functional.resample
+    taps, width, up, down = pn.resample_taps(24000, 16000)
+    x = torch.randn(2, 5001, generator=torch.Generator().manual_seed(0))
+    xp = torch.nn.functional.pad(x, (width, width + down))
+    n_out = -(-up * x.shape[1] // down)
+    y = torch.stack([sum(taps[i % up, k] * xp[:, (i // up) * down + k] for k in range(taps.shape[1]))
+                     for i in range(0, n_out, 97)], dim=1)
+    assert (y - torchaudio.functional.resample(x, 24000, 16000)[:, ::97]).abs().max() < 1e-5
+
+    window, banks, rng = pn.kaldi_fbank_tables()
+    want_banks, _ = kaldi.get_mel_banks(80, 512, 16000.0, 20.0, 0.0, 100.0, -500.0, 1.0)
+    assert torch.equal(banks[:, :256], want_banks) and banks[:, 256].abs().max() == 0
+    assert torch.equal(window, kaldi._feature_window_function("povey", 400, 0.42, torch.device("cpu"), torch.float32))
+    for m in range(80):
+        nz = torch.nonzero(banks[m]).flatten()
+        assert nz.min() >= rng[m, 0] and nz.max() < rng[m, 1]
+
+
+def test_mel_filterbank_matches_torchaudio():
+    import torchaudio
+
+    from lemas_tts import ops
+
+    fb, rng = ops.mel_filterbank(100, 24000, 1024)
+    want = torchaudio.functional.melscale_fbanks(513, 0.0, 12000.0, 100, 24000, norm=None, mel_scale="htk")
+    assert torch.equal(fb, want)
+    for m in range(100):
+        nz = torch.nonzero(want[:, m]).flatten()
+        assert nz.min() >= rng[m, 0] and nz.max() < rng[m, 1]
