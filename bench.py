@@ -441,7 +441,8 @@ def run_b200(args):
                      "achieved": att_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": att_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                      "flops_per_launch": att_flops, "launch_ms": att_ms / att_n if att_n else None,
-                     "note": "head dim 64: 16 exp2/clk/SM (measured) caps the tensor pipe near 50 % — see DESIGN.md §6"},
+                     "note": "head dim 64: a 128x128 score block needs 1024 SFU clk (16 exp2/clk/SM, measured) against 512 MMA clk; "
+                             "P is kept in TMEM (TS-form P V) and 1/4 of the exp2 run on the FMA pipe — see DESIGN.md §6"},
         "sampler_tensor_frac": dit_flops / sec_step / 1e12 / pk["tflops"],
         "kernels": kinds, "profiled_step_ms": prof_ms,
         "clocks": clocks,
