@@ -38,12 +38,15 @@ DEVI void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
 DEVI void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug must trap (process gets a launch failure) instead of hanging the GPU box.
-#ifndef LEMAS_MBAR_SPIN_LIMIT
-#define LEMAS_MBAR_SPIN_LIMIT (1u << 24)
+// Bounded wait: a protocol bug must trap (process gets a launch failure) instead of hanging the GPU box.  The bound
+// is wall time on the SM clock (~2 s at 2 GHz), checked every 256 polls: a try_wait may suspend the thread for an
+// implementation-defined time, so a poll count alone says little about elapsed time.
+#ifndef LEMAS_MBAR_TIMEOUT_CLK
+#define LEMAS_MBAR_TIMEOUT_CLK 4000000000ll
 #endif
 DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  long long t0 = 0;
   while (true) {
     uint32_t ok;
     asm volatile(
@@ -52,10 +55,14 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
-    if (++spins > LEMAS_MBAR_SPIN_LIMIT) {
-      printf("lemas: mbarrier wait timed out (block %d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, (void*)bar, parity);
-      __trap();
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > LEMAS_MBAR_TIMEOUT_CLK) {
+        printf("lemas: mbarrier wait timed out (block %d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y,
+               threadIdx.x, (void*)bar, parity);
+        __trap();
+      }
     }
   }
 }
@@ -183,6 +190,7 @@ DEVI void mbar_arrive_cluster(uint32_t cluster_addr) {
 }
 DEVI void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  long long t0 = 0;
   while (true) {
     uint32_t ok;
     asm volatile(
@@ -191,9 +199,13 @@ DEVI void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
-    if (++spins > LEMAS_MBAR_SPIN_LIMIT) {
-      printf("lemas: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > LEMAS_MBAR_TIMEOUT_CLK) {
+        printf("lemas: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -289,16 +301,40 @@ DEVI void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "
 }  // namespace lemas
 
 namespace lemas {
-// Lean variants on 32-bit shared-window addresses, for hot loops: no generic->shared conversion per call, and the
-// wait has no spin bound (use only where another role of the same CTA keeps a bounded mbar_wait — a protocol bug
-// then still traps the kernel instead of hanging the GPU).
+// Lean variants on 32-bit shared-window addresses, for hot loops: no generic->shared conversion per call.  The fast
+// path is one try_wait; a miss drops into an out-of-line loop that polls just as tightly but checks the SM clock
+// every 256 polls and traps after LEMAS_MBAR_TIMEOUT_CLK — a lapped parity wait (see attention.cu, dead-row warps)
+// must end the kernel with an error, never hang the GPU.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+    if (ok) return;
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > LEMAS_MBAR_TIMEOUT_CLK) {
+        printf("lemas: mbarrier wait timed out (block %d,%d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x, bar_addr, parity);
+        __trap();
+      }
+    }
+  }
+}
 DEVI void mbar_wait_lean(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "LEMAS_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra LEMAS_WAIT_%=;\n\t}\n"
-      ::"r"(bar_addr), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
+  if (!ok) mbar_wait_slow(bar_addr, parity);
 }
 DEVI void mbar_arrive_s(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");

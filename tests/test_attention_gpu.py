@@ -46,3 +46,29 @@ def test_attention_matches_fp32(B, N, H, ragged):
         got, ref = got[rows], ref[rows]
     err = (got - ref).abs().max().item()
     assert math.isfinite(err) and err < 4e-3, f"max abs err {err}"
+
+
+@pytest.mark.timeout(120)
+def test_attention_multiwave_back_to_back_launches():
+    """Regression (round 1): 2 x 16 x 18 = 576 CTAs (two waves on 148 SMs x 2) launched back to back, last query tile
+    with three all-padding warps per key half.  Their lanes polled the barrier independently, lane 0 ran ahead and the
+    parity wait of the others was lapped -> the kernel hung.  Must finish, and every launch must give the same bits."""
+    from lemas_tts import ops
+
+    B, N, H = 2, 2187, 16
+    g = torch.Generator().manual_seed(7)
+    qk = (torch.randn(B * N, 2 * H * 64, generator=g) * 1.5).cuda().half()
+    npad = (N + 63) // 64 * 64
+    vt = torch.randn(B, H, 64, npad, generator=g).cuda().half()
+    first = ops.attention(qk, vt, B, N, H, None).clone()
+    for _ in range(30):
+        out = ops.attention(qk, vt, B, N, H, None)
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+    kv_len = torch.tensor([N, 700], device="cuda", dtype=torch.int32)   # ragged: early-exit tiles + partial blocks
+    a = ops.attention(qk, vt, B, N, H, kv_len).clone()
+    for _ in range(10):
+        b = ops.attention(qk, vt, B, N, H, kv_len)
+    torch.cuda.synchronize()
+    rows = (torch.arange(N, device="cuda")[None] < kv_len[:, None]).reshape(-1)
+    assert torch.equal(a[rows], b[rows])
