@@ -118,25 +118,17 @@ class CFM(nn.Module):
     # ------------------------------------------------------------------------------------------------
     def _prosody_embeds(self, raw_audio: torch.Tensor, device) -> torch.Tensor:
         """cfm.py:248-262: per-sample 24k -> 16k resample, kaldi fbank, ECAPA-TDNN -> [B, 512]."""
-        import torchaudio
+        from lemas_tts import _native as nv
+        from lemas_tts import prosody_native as pn
 
-        from .backbones.prosody_encoder import extract_fbank_16k
-
+        nv.require_device()   # no CPU path: raises "CUDA error: ..." like every other stage of sample()
         src_sr = self.mel_spec.target_sample_rate
         raw_audio = raw_audio.to(device=device, dtype=torch.float32)
-        if raw_audio.is_cuda:
-            # The reference encodes one utterance at a time over the whole (padded) row raw_audio[b]; every stage is
-            # per-sample, so the rows of the batch go through the native kernels together with the same result:
-            # polyphase resampler -> kaldi fbank -> ECAPA-TDNN (csrc/prosody.cu).
-            from lemas_tts import prosody_native as pn
-            audio_16k = pn.resample(raw_audio.contiguous(), src_sr, 16_000)
-            return self.prosody_encoder(pn.kaldi_fbank_80(audio_16k), padding_mask=None)
-        fbanks = []
-        for b in range(raw_audio.shape[0]):
-            audio_b = raw_audio[b].unsqueeze(0)
-            audio_16k = (torchaudio.functional.resample(audio_b, src_sr, 16_000) if src_sr != 16_000 else audio_b)
-            fbanks.append(extract_fbank_16k(audio_16k.squeeze(0)).to(device=device, dtype=torch.float32))
-        return torch.stack([self.prosody_encoder(f.unsqueeze(0), padding_mask=None)[0] for f in fbanks], dim=0)
+        # The reference encodes one utterance at a time over the whole (padded) row raw_audio[b]; every stage is
+        # per-sample, so the rows of the batch go through the native kernels together with the same result:
+        # polyphase resampler -> kaldi fbank -> ECAPA-TDNN (csrc/prosody.cu).
+        audio_16k = pn.resample(raw_audio.contiguous(), src_sr, 16_000)
+        return self.prosody_encoder(pn.kaldi_fbank_80(audio_16k), padding_mask=None)
 
     @torch.no_grad()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None,
