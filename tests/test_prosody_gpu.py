@@ -81,3 +81,22 @@ def test_prosody_embeds_end_to_end_matches_cpu_chain():
         from lemas_tts import prosody_native as pn
         got = enc.cuda()(pn.kaldi_fbank_80(pn.resample(raw.cuda(), 24000, 16000))).cpu()
     assert (got - want).abs().max().item() < 5e-5
+
+
+def test_native_embeddings_match_verbatim_reference_golden(tmp_path):
+    """The whole native chain (resampler -> kaldi fbank -> ECAPA-TDNN) against embeddings minted by the VERBATIM
+    reference modules (oracle/gen_golden.py, tests/golden/sample_tiny_prosody.pt)."""
+    import golden_cases as gc
+
+    from lemas_tts import prosody_native as pn
+    from lemas_tts.model.backbones.prosody_encoder import ProsodyEncoder
+
+    case = gc.PROSODY_CASE
+    gold = gc.load(case["name"])
+    _, audio, _, _, _ = gc.prosody_inputs(case)
+    cfg_path, ckpt_path = syn.write_prosody_assets(tmp_path, syn.TINY_PROSODY_CFG, seed=case["pseed"])
+    enc = ProsodyEncoder(cfg_path, ckpt_path).eval().cuda()
+    with torch.no_grad():
+        got = enc(pn.kaldi_fbank_80(pn.resample(audio.cuda().float().contiguous(), 24000, 16000))).cpu()
+    assert got.shape == gold["embeds"].shape
+    assert (got - gold["embeds"]).abs().max().item() < 2e-5
