@@ -113,6 +113,19 @@ def kaldi_fbank_80(wav16k: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ ECAPA-TDNN
+def tdnn_layout(m) -> dict:
+    """TDNNBlock parameters in the layout conv_cl_kernel reads: weight [cout, cin/groups, k] -> [k, cin/groups, cout]."""
+    conv = m.conv
+    return dict(w=conv.weight.detach().permute(2, 1, 0).contiguous(), b=conv.bias.detach(),
+                ln_w=m.norm.weight.detach(), ln_b=m.norm.bias.detach(), cin=conv.in_channels, cout=conv.out_channels,
+                k=conv.kernel_size[0], dil=conv.dilation[0], groups=conv.groups)
+
+
+def dense_layout(conv):
+    """1x1 Conv1d as a dense layer: weight [cout, cin, 1] -> [cin, cout]."""
+    return conv.weight.detach()[:, :, 0].t().contiguous(), conv.bias.detach()
+
+
 class PackedEcapa:
     """fp32 device copies of the encoder's parameters in the layouts csrc/prosody.cu reads, plus the ABI structs."""
 
@@ -163,16 +176,14 @@ class PackedEcapa:
 
     def _tdnn(self, m):
         s = nv.ProsodyTdnn()
-        conv = m.conv
-        s.w = self._t(conv.weight.detach().permute(2, 1, 0))      # [cout, cin_g, k] -> [k, cin_g, cout]
-        s.b = self._t(conv.bias)
-        s.ln_w, s.ln_b = self._t(m.norm.weight), self._t(m.norm.bias)
-        s.cin, s.cout, s.k = conv.in_channels, conv.out_channels, conv.kernel_size[0]
-        s.dil, s.groups = conv.dilation[0], conv.groups
+        lay = tdnn_layout(m)
+        s.w, s.b, s.ln_w, s.ln_b = (self._t(lay[k]) for k in ("w", "b", "ln_w", "ln_b"))
+        s.cin, s.cout, s.k, s.dil, s.groups = lay["cin"], lay["cout"], lay["k"], lay["dil"], lay["groups"]
         return s
 
     def _dense(self, conv):
-        return self._t(conv.weight.detach()[:, :, 0].t()), self._t(conv.bias)   # [cout, cin, 1] -> [cin, cout]
+        w, b = dense_layout(conv)
+        return self._t(w), self._t(b)
 
 
 def ecapa_encode(enc, fbank: torch.Tensor) -> torch.Tensor:

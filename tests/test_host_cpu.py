@@ -196,3 +196,77 @@ def test_mel_filterbank_matches_torchaudio():
     for m in range(100):
         nz = torch.nonzero(want[:, m]).flatten()
         assert nz.min() >= rng[m, 0] and nz.max() < rng[m, 1]
+
+
+def test_native_ecapa_dataflow_restated_on_cpu(tmp_path):
+    """csrc/prosody.cu's data flow (lemas_prosody_encode) restated step by step in torch on the PACKED layouts the
+    kernels read — channels-last activations, [k][cin/groups][cout] conv weights, Res2Net groups and the MFA
+    concatenation as column slices of one buffer — against the reference's module arithmetic.  Pins the packing and
+    the wiring without a GPU; the kernels themselves are checked in tests/test_prosody_gpu.py."""
+    from lemas_tts import prosody_native as pn
+    from lemas_tts.model.backbones.prosody_encoder import ProsodyEncoder
+
+    cfg_path, ckpt_path = syn.write_prosody_assets(tmp_path, syn.TINY_PROSODY_CFG, seed=3)
+    enc = ProsodyEncoder(cfg_path, ckpt_path).eval().encoder
+
+    def conv_cl(x, lay, add=None, act="relu"):          # x: [b, t, cin] channels-last, zero "same" padding
+        if add is not None:
+            x = x + add
+        b, t, _ = x.shape
+        k, dil, g = lay["k"], lay["dil"], lay["groups"]
+        cin_g, cout_g = lay["cin"] // g, lay["cout"] // g
+        y = torch.zeros(b, t, lay["cout"])
+        for tap in range(k):
+            shift = (tap - (k - 1) // 2) * dil
+            xs = torch.zeros_like(x)
+            lo, hi = max(0, -shift), min(t, t - shift)
+            if hi > lo:
+                xs[:, lo:hi] = x[:, lo + shift:hi + shift]
+            for gi in range(g):
+                y[:, :, gi * cout_g:(gi + 1) * cout_g] += xs[:, :, gi * cin_g:(gi + 1) * cin_g] @ \
+                    lay["w"][tap][:, gi * cout_g:(gi + 1) * cout_g]
+        y = y + lay["b"]
+        return {"relu": torch.relu, "none": lambda v: v}[act](y)
+
+    def tdnn(x, m, add=None, after=None):
+        lay = pn.tdnn_layout(m)
+        y = torch.nn.functional.layer_norm(conv_cl(x, lay, add), (lay["cout"],), lay["ln_w"], lay["ln_b"], 1e-12)
+        return after(y) if after else y
+
+    def dense(x, conv, act):
+        w, b = pn.dense_layout(conv)
+        return act(x @ w + b)
+
+    g = torch.Generator().manual_seed(5)
+    fbank = torch.randn(2, 41, 80, generator=g) * 2 + 3
+    with torch.no_grad():
+        blocks = list(enc.blocks)
+        c = enc.channels[0]
+        cg = c // 8
+        x = tdnn(fbank, blocks[0])
+        cat = torch.zeros(2, 41, c * (len(blocks) - 1))
+        for bi, blk in enumerate(blocks[1:]):
+            t1 = tdnn(x, blk.tdnn1)
+            y = torch.zeros_like(t1)
+            y[:, :, :cg] = t1[:, :, :cg]
+            for i in range(1, 8):
+                add = y[:, :, (i - 1) * cg:i * cg] if i >= 2 else None
+                y[:, :, i * cg:(i + 1) * cg] = tdnn(t1[:, :, i * cg:(i + 1) * cg], blk.res2net_block.blocks[i - 1], add)
+            t2 = tdnn(y, blk.tdnn2)
+            s = dense(dense(t2.mean(1), blk.se_block.conv1, torch.relu), blk.se_block.conv2, torch.sigmoid)
+            cat[:, :, bi * c:(bi + 1) * c] = s[:, None, :] * t2 + x
+            x = cat[:, :, bi * c:(bi + 1) * c]
+        mfa = tdnn(cat, enc.mfa)
+        mean = mfa.mean(1)
+        std = ((mfa - mean[:, None]) ** 2).mean(1).clamp(1e-12).sqrt()
+        concat = torch.cat([mfa, mean[:, None].expand_as(mfa), std[:, None].expand_as(mfa)], dim=2)
+        a1 = tdnn(concat, enc.asp.tdnn, after=torch.tanh)
+        logits = dense(a1, enc.asp.conv, lambda v: v)
+        attn = torch.softmax(logits, dim=1)
+        pm = (attn * mfa).sum(1)
+        ps = (attn * (mfa - pm[:, None]) ** 2).sum(1).clamp(1e-12).sqrt()
+        pooled = torch.nn.functional.layer_norm(torch.cat([pm, ps], 1), (2 * mfa.shape[2],), enc.asp_norm.weight,
+                                                enc.asp_norm.bias, 1e-12)
+        emb = torch.nn.functional.normalize(dense(pooled, enc.fc, lambda v: v), dim=-1)
+        want = enc.forward_torch(fbank)
+    assert (emb - want).abs().max() < 2e-5
