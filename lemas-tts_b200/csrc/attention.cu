@@ -34,8 +34,7 @@
 // the QKV GEMM epilogue writes, so both MMAs use K-major operands.
 #include <type_traits>
 
-#include "common.h"
-#include "ptx.cuh"
+#include "att_common.cuh"
 
 namespace lemas {
 
@@ -65,90 +64,6 @@ constexpr float ATT_RESCALE_LOG2 = 8.0f;  // advance the reference max only past
 #endif
 #ifndef ATT_DEPHASE_CLK
 #define ATT_DEPHASE_CLK 1000              // head start of key half A over key half B (about half a block period)
-#endif
-
-struct AttnParams {
-  long long* trace;   // debug: clock64 stamps (tools/trace_att.py); nullptr in production
-  const int* kv_len;
-  __half* out;
-  int seq, heads, inner;
-};
-
-DEVI float fmax3f(float a, float b, float c) {  // 3-input max: one FMNMX3 on sm_100
-  float y;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
-  return y;
-}
-DEVI float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes of arithmetic.
-DEVI uint64_t f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-DEVI void f32x2_split(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-DEVI uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-DEVI uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x (K/2) columns of packed fp16 pairs (row-major along K).
-DEVI void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-#ifdef LEMAS_ATT_DEBUG  // hang hunting: every wait has a deadline; a waiter that misses it records who it is in
-                        // (pinned host) memory at p.trace and traps.  tools/att_hang_probe.py --debug
-DEVI void dbg_wait(long long* dbg, uint32_t bar_addr, uint32_t parity, int tag, int j) {
-  bool done = false;
-  for (int outer = 0; outer < 200000 && !done; ++outer) {   // same tight polling as the production waits
-#pragma unroll 1
-    for (int inner = 0; inner < 64; ++inner) {
-      uint32_t ok;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}\n"
-          : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
-      if (ok) { done = true; break; }
-    }
-  }
-  if (done) return;
-  if ((threadIdx.x & 31) == 0 || tag < 8) {
-    const int slot = atomicAdd(reinterpret_cast<int*>(dbg), 1);
-    if (slot < 500) {
-      long long* r = dbg + 1 + slot * 4;
-      unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      r[0] = (long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      r[1] = threadIdx.x >> 5;
-      r[2] = tag * 1000 + j;
-      r[3] = smid;
-    }
-    __threadfence_system();
-  }
-  const long long t2 = clock64() + 4000000ll;
-  while (clock64() < t2) { }
-  __trap();
-}
-#define ATT_WAIT_P(barptr, parity, tag, j) dbg_wait(p.trace, smem_u32(barptr), parity, tag, j)
-#define ATT_WAIT_A(addr, parity, tag, j) dbg_wait(p.trace, addr, parity, tag, j)
-#else
-#define ATT_WAIT_P(barptr, parity, tag, j) mbar_wait(barptr, parity)
-#define ATT_WAIT_A(addr, parity, tag, j) mbar_wait_lean(addr, parity)
 #endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -483,15 +398,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 
 using namespace lemas;
 
-static long long* g_att_trace = nullptr;
-// debug aid (not part of the public header): device buffer of 8 warps x 32 blocks x 8 int64 clock stamps
-extern "C" void lemas_debug_attention_trace(void* buf) { g_att_trace = static_cast<long long*>(buf); }
-
-extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
-                                   void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
-  LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
-  LEMAS_REQUIRE(ld_qk % 8 == 0 && vt_ld % 8 == 0 && vt_ld >= seq, "lemas_attention_f16: ld_qk/vt_ld must be multiples of 8");
-  LEMAS_REQUIRE(batch >= 1 && seq >= 1 && heads >= 1, "lemas_attention_f16: bad shape");
+// v3 launcher (one 128-query tile per CTA, two CTAs per SM).  The public entry point lemas_attention_f16 lives in
+// attention5.cu and dispatches between this kernel and the persistent two-tile kernel.
+int lemas::attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
+                               void* out16, int32_t batch, int32_t seq, int32_t heads, long long* trace, void* stream) {
   const int inner = heads * ATT_D;
   CUtensorMap tmQK, tmVT;
   {
@@ -508,8 +418,8 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   }
   static unsigned long long configured = 0;
   LEMAS_CUDA_OK(ensure_dynamic_smem(attention_kernel, ATT_SMEM, configured));
-  AttnParams p;
-  p.trace = g_att_trace;
+  AttnParams p = {};
+  p.trace = trace;
   p.kv_len = kv_len;
   p.out = static_cast<__half*>(out16);
   p.seq = seq;

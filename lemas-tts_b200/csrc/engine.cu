@@ -340,7 +340,9 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
     LEMAS_CUDA_OK(cudaMemcpyAsync(a->trajectory, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
   const int* kv2 = a->kv_len ? b.kv_len2 : nullptr;
 
-  const bool want_graph = a->use_graph && !e->profile && a->steps >= 3 && a->trajectory == nullptr;
+  // the trajectory slot is indexed by the device-side step counter, so a requested trajectory replays too; its
+  // pointer is captured, hence part of the cache key (the Python side passes a persistent staging buffer)
+  const bool want_graph = a->use_graph && !e->profile && a->steps >= 3;
   if (!want_graph) {
     for (int i = 0; i < a->steps; ++i) LEMAS_TRY(ode_step(e, b, a, variants, kv2, a->y, st));
     return LEMAS_OK;
@@ -352,7 +354,8 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   for (auto& cand : e->graphs)
     if (cand.batch == a->batch && cand.seq == a->seq && cand.steps == a->steps && cand.variants == variants &&
         cand.has_kv == (kv2 != nullptr) &&
-        cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope)
+        cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope &&
+        cand.traj == a->trajectory)
       g = &cand;
   int first_replayed = 0;
   if (!g) {

@@ -176,7 +176,35 @@ def ptr(t: torch.Tensor | None):
 
 
 def stream() -> int:
+    """Raw handle of the CURRENT device's current stream — call it inside `on_device` (below)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(fn):
+    """Run a native call on the device that owns its operands: the first CUDA tensor among the arguments, else the
+    `.device` of `self`.  The library launches on the current device with the stream it is handed, and the reference
+    API accepts any device string (`TTS(device="cuda:1")`, api.py:94) without a prior torch.cuda.set_device — so the
+    wrapper, not the caller, selects the device (and thereby the stream `stream()` returns)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        if args and not isinstance(args[0], torch.Tensor):  # engine method: the engine's own device wins
+            d = getattr(args[0], "device", None)
+            if isinstance(d, torch.device) and d.type == "cuda":
+                dev = d
+        if dev is None:
+            for a in list(args) + list(kwargs.values()):
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    dev = a.device
+                    break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
 
 
 def require_device() -> None:
@@ -185,3 +213,20 @@ def require_device() -> None:
     if not load().lemas_device_supported():
         raise RuntimeError("CUDA error: no kernel image is available for execution on the device "
                            "(liblemas_b200 is built for sm_100a only)")
+
+
+def weights_key(module) -> tuple:
+    """Cache key of the packed (fp16 / re-laid-out) copy of a module's weights: device, storage addresses and the
+    in-place version counters of EVERY parameter and buffer — an EMA `p.data.copy_`, a partial load or a
+    `torch.nn.utils` helper on any tensor invalidates the packed copy, not only a change of one sentinel weight.
+    Tensors created under torch.inference_mode() have no version counter; their address still takes part."""
+    ver, ptrs, n, dev = 0, 0, 0, None
+    for t in list(module.parameters()) + list(module.buffers()):
+        try:
+            ver += t._version
+        except RuntimeError:
+            pass
+        ptrs = (ptrs * 1000003 + t.data_ptr()) & 0xFFFFFFFFFFFFFFFF
+        n += 1
+        dev = t.device
+    return (str(dev), n, ver, ptrs)

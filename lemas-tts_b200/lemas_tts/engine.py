@@ -130,6 +130,7 @@ class DiTEngine:
         ang = torch.outer(torch.arange(4096, dtype=f32), inv_freq.detach().float().cpu())
         self._rope = torch.stack((ang.cos(), ang.sin()), dim=-1).to(dv).contiguous()  # [4096, 32, 2]
         self._ws = None
+        self._traj = None  # persistent trajectory staging buffer (stable address for the step graph)
 
     def __del__(self):
         h = getattr(self, "_handle", None)
@@ -175,6 +176,7 @@ class DiTEngine:
         a.use_graph = int(use_graph)
         return a
 
+    @nv.on_device
     def sample_loop(self, y: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor | None,
                     t_grid: torch.Tensor, cfg_strength: float, kv_len: torch.Tensor | None = None,
                     trajectory: torch.Tensor | None = None, use_graph: bool = True) -> torch.Tensor:
@@ -183,14 +185,28 @@ class DiTEngine:
         tg = t_grid.detach().to("cpu", f32).contiguous()
         steps = tg.numel() - 1
         t_host = (C.c_float * (steps + 1))(*tg.tolist())
-        a = self._args(y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength, trajectory, use_graph)
+        # The step graph captures the trajectory pointer: stage the states in a persistent buffer (stable address ->
+        # graph cache hit on every call) and copy them out, instead of falling back to eager launches whenever the
+        # reference-default call (trajectory returned, cfm.py:456) is made.
+        stage = None
+        if trajectory is not None and use_graph and steps >= 3:
+            n = trajectory.numel()
+            if self._traj is None or self._traj.numel() < n:
+                self._traj = None
+                self._traj = torch.empty(n, device=self.device, dtype=f32)
+            stage = self._traj[:n].view(trajectory.shape)
+        a = self._args(y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength,
+                       stage if stage is not None else trajectory, use_graph)
         nv.check(nv.load().lemas_sampler_run(self._handle, C.byref(a), nv.stream()))
+        if stage is not None:
+            trajectory.copy_(stage)
         return y
 
     def profile(self, enable: bool) -> None:
         """Bracket every sampler launch with CUDA events (measurement aid, see lemas_engine_profile)."""
         nv.check(nv.load().lemas_engine_profile(self._handle, int(enable)))
 
+    @nv.on_device
     def profile_read(self) -> dict:
         """{kind: (milliseconds, launches)} accumulated since the last read; synchronises the current stream."""
         n = len(nv.PROF_KINDS)
@@ -198,6 +214,7 @@ class DiTEngine:
         nv.check(nv.load().lemas_engine_profile_read(self._handle, ms, cnt, nv.stream()))
         return {k: (ms[i], cnt[i]) for i, k in enumerate(nv.PROF_KINDS)}
 
+    @nv.on_device
     def forward_pair(self, x: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor,
                      t: float, kv_len: torch.Tensor | None = None, want_hidden: bool = False):
         """One DiT.forward (dit.py:194-254) for the conditional and the unconditional variant at once.
@@ -271,6 +288,7 @@ class VocosEngine:
         self._weights = w
         self._ws = None
 
+    @nv.on_device
     def decode(self, mel: torch.Tensor) -> torch.Tensor:
         """Vocos.decode (utils_infer.py:549): mel [B, in_ch, T] -> wav [B, (T-1)*256] fp32."""
         if mel.dim() != 3 or mel.shape[1] != self.in_ch:
@@ -307,6 +325,7 @@ class TextEngine:
         w = nv.TextWeights()
         w.dim, w.inter, w.layers, w.mask_padding = text_dim, 2 * text_dim, conv_layers, int(mask_padding)
         w.table = nv.ptr(hold(_dev(sd[p + "text_embed.weight"], dv, f32)))
+        self.table_rows = int(sd[p + "text_embed.weight"].shape[0])
         if conv_layers > 0:
             inv = 1.0 / (10000.0 ** (torch.arange(0, text_dim, 2)[: text_dim // 2].float() / text_dim))
             ang = torch.outer(torch.arange(4096), inv).float()
@@ -331,11 +350,17 @@ class TextEngine:
         self._weights = w
         self._ws = None
 
+    @nv.on_device
     def embed(self, ids: torch.Tensor, drop: torch.Tensor) -> torch.Tensor:
         """ids: int32 [B, N] (shifted by +1, 0 = filler); drop: uint8 [B] -> fp32 [B, N, dim]."""
         B, N = ids.shape
         ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
         drop = drop.to(device=self.device, dtype=torch.uint8).contiguous()
+        # nn.Embedding in the reference (dit.py:62) faults on an id outside the table (vocab.txt that does not match the
+        # checkpoint, caller-supplied token tensor); the gather kernel must never read out of bounds silently.  Same
+        # contract as torch on CUDA: an asynchronous device-side assertion, no host synchronisation.
+        torch._assert_async(((ids >= 0) & (ids < self.table_rows)).all(),
+                            f"index out of range in TextEmbedding: ids must lie in [0, {self.table_rows})")
         need = int(nv.load().lemas_text_workspace_bytes(C.byref(self._weights), B, N))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None

@@ -15,6 +15,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from ... import _native as nv
+
 from ..modules import (AdaLayerNorm, ConvNeXtV2Block, ConvPositionEmbedding, DiTBlock, TimestepEmbedding,
                        precompute_freqs_cis)
 
@@ -68,7 +70,7 @@ class TextEmbedding(nn.Module):
     def native(self):
         """Weights packed for lemas_text_embedding (once per weight version / device)."""
         w = self.text_embed.weight
-        key = (str(w.device), w._version, w.data_ptr())
+        key = nv.weights_key(self)
         if getattr(self, "_native", None) is None or self._native_key != key:
             from ...engine import TextEngine
 
@@ -181,7 +183,7 @@ class DiT(nn.Module):
     def engine(self):
         """Pack the current parameters for liblemas_b200.so (once per weight version / device)."""
         dev = self.proj_out.weight.device
-        key = (str(dev), self.proj_out.weight._version, self.proj_out.weight.data_ptr())
+        key = nv.weights_key(self)
         if self._engine is None or self._engine_key != key:
             if dev.type != "cuda":
                 raise RuntimeError("CUDA error: the lemas_tts B200 build has no CPU path; move the model to a "

@@ -19,6 +19,7 @@ def _chk(t: torch.Tensor, dtype, name: str):
         raise ValueError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
 
 
+@nv.on_device
 def gemm(a16: torch.Tensor, w16: torch.Tensor, *, epilogue: int, n: int | None = None, bias=None, block_n: int = 128,
          out16=None, out32=None, resid=None, gate=None, gate_bstride: int = 0, row_valid=None, seq_len: int | None = None,
          rope=None, rope_cols: int = 0, inner: int = 0, vt=None, taps: int = 1, tap_pad: int = 0,
@@ -55,6 +56,7 @@ def gemm(a16: torch.Tensor, w16: torch.Tensor, *, epilogue: int, n: int | None =
     nv.check(nv.load().lemas_gemm_f16(d, nv.stream()))
 
 
+@nv.on_device
 def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, seq_len: int | None = None) -> torch.Tensor:
     """x: [rows, dim] fp32; scale/shift: [dim] or [batch, dim] fp32 -> fp16 [rows, dim]."""
     nv.require_device()
@@ -67,6 +69,7 @@ def ln_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, seq_l
     return out
 
 
+@nv.on_device
 def ln_affine(x, weight, bias, eps=1e-6, want16=True, want32=False):
     nv.require_device()
     _chk(x, f32, "x")
@@ -78,6 +81,7 @@ def ln_affine(x, weight, bias, eps=1e-6, want16=True, want32=False):
     return o16, o32
 
 
+@nv.on_device
 def attention(qk16: torch.Tensor, vt16: torch.Tensor, batch: int, seq: int, heads: int, kv_len=None) -> torch.Tensor:
     """qk16: [batch*seq, 2*heads*64] fp16 (q | k); vt16: [batch, heads, 64, vt_ld] fp16 -> [batch*seq, heads*64]."""
     nv.require_device()
@@ -89,6 +93,7 @@ def attention(qk16: torch.Tensor, vt16: torch.Tensor, batch: int, seq: int, head
     return out
 
 
+@nv.on_device
 def skinny_linear(x, w, b, act_in=False, act_out=False):
     nv.require_device()
     _chk(x, f32, "x")
@@ -101,6 +106,7 @@ def skinny_linear(x, w, b, act_in=False, act_out=False):
     return y
 
 
+@nv.on_device
 def time_sinusoid(t: torch.Tensor) -> torch.Tensor:
     nv.require_device()
     _chk(t, f32, "t")
@@ -109,6 +115,7 @@ def time_sinusoid(t: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@nv.on_device
 def cfg_euler(pred, y, x16, t: float, dt: float, cfg_strength: float, copies: int, traj=None):
     nv.require_device()
     rows, mel = y.shape[0] * y.shape[1] if y.dim() == 3 else y.shape[0], y.shape[-1]
@@ -116,6 +123,7 @@ def cfg_euler(pred, y, x16, t: float, dt: float, cfg_strength: float, copies: in
                                        nv.ptr(traj), rows, mel, t, dt, cfg_strength, nv.stream()))
 
 
+@nv.on_device
 def dwconv7_ln(x, dw_w, dw_b, ln_w, ln_b):
     """x: [b, t, dim] fp32; dw_w: [7, dim] fp32 -> fp16 [b, t, dim]."""
     nv.require_device()
@@ -150,6 +158,7 @@ def mel_filterbank(n_mels: int = 100, sample_rate: int = 24000, n_fft: int = 102
     return fb, torch.stack((first, last), dim=1).to(torch.int32).contiguous()
 
 
+@nv.on_device
 def mel_spectrogram_1024(wav: torch.Tensor, n_mels: int = 100, sample_rate: int = 24000) -> torch.Tensor:
     """wav: fp32 [b, nw] on the GPU -> log-mel fp32 [b, n_mels, nw//256 + 1]   (modules.py:75-101, csrc/frontend.cu)."""
     nv.require_device()
@@ -167,6 +176,7 @@ def mel_spectrogram_1024(wav: torch.Tensor, n_mels: int = 100, sample_rate: int 
     return mel
 
 
+@nv.on_device
 def istft_1024(head: torch.Tensor, batch: int, t: int) -> torch.Tensor:
     """head: [batch*t, ld>=1026] fp32 rows (log-mag | phase) -> wav [batch, (t-1)*256]."""
     nv.require_device()

@@ -58,3 +58,91 @@ def max_over_ranks(value: float, device="cpu", group=None) -> float:
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------- sharded synthesis
+#
+# BASELINE.json configs[3] / SURVEY.md §8e: a LIST of independent utterances is dealt to the ranks by
+# `shard_utterances`, every rank runs CFM.sample + Vocos.decode on its own utterances (the reference's B > 1 path,
+# cfm.py:336-339), and the waveforms are gathered on the host.  No collective touches the data path.
+#
+# Sharding must not change a single bit of any utterance.  The reference's batch padding is
+# "leaky" (an utterance padded inside a longer batch differs from its solo run), so utterances are only
+# ever batched with utterances of the SAME shape (reference frames, total frames): such a batch has no padding, every
+# kernel tiles per sequence, and a row's result does not depend on which or how many other rows share the launch.
+# The noise of utterance i is drawn from its own generator seeded with (seed, i), independent of rank and batch.
+
+
+def utterance_noise(seed: int, index: int, frames: int, mel_dim: int, device) -> torch.Tensor:
+    """y0 of utterance `index` (cfm.py:430-435 draws randn(duration, mel) per row): a per-utterance device generator,
+    so the draw does not depend on how the list is sharded or batched."""
+    g = torch.Generator(device=device)
+    g.manual_seed((int(seed) * 1_000_003 + int(index)) & 0x7FFFFFFFFFFFFFFF)
+    return torch.randn(frames, mel_dim, generator=g, device=device, dtype=torch.float32)
+
+
+def make_synth_fn(model, vocoder, *, steps: int = 32, cfg_strength: float = 2.0, sway_sampling_coef=3.0, seed: int = 0,
+                  batch_size: int = 32, use_acc_grl: bool = False):
+    """Binds a CFM model and a vocoder into the callable `synthesize_sharded` drives:
+    fn([(global_index, utterance), ...]) -> {global_index: waveform (1-D fp32, CPU)}.
+    An utterance is a dict: cond = reference mel [Tc, mel] (fp32), text = token ids [nt] (int64, no padding),
+    duration = total frames N."""
+    device = model.device
+    mel_dim = model.num_channels
+
+    def fn(items):
+        groups: dict[tuple, list] = {}
+        for idx, u in items:  # same (Tc, N) only: no padding inside a batch (see the header)
+            groups.setdefault((int(u["cond"].shape[0]), int(u["duration"])), []).append((idx, u))
+        out = {}
+        for (tc, n), members in sorted(groups.items()):
+            for i in range(0, len(members), batch_size):
+                chunk = members[i:i + batch_size]
+                cond = torch.stack([u["cond"] for _, u in chunk]).to(device, torch.float32)
+                nt = max(int(u["text"].numel()) for _, u in chunk)
+                text = torch.full((len(chunk), nt), -1, dtype=torch.long)
+                for r, (_, u) in enumerate(chunk):
+                    text[r, : u["text"].numel()] = u["text"]
+                dur = max(n, tc + 1, nt + 1)  # cfm.py:300 raises the duration; the noise must match the final length
+                noise = torch.stack([utterance_noise(seed, idx, min(dur, 4096), mel_dim, device) for idx, _ in chunk])
+                mel, _ = model.sample(cond=cond, text=text.to(device), duration=n, steps=steps,
+                                      cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, noise=noise,
+                                      use_acc_grl=use_acc_grl, use_prosody_encoder=False, return_trajectory=False)
+                wav = vocoder.decode(mel[:, tc:, :].permute(0, 2, 1))  # utils_infer.py:545-549
+                wav = wav.cpu()
+                for r, (idx, _) in enumerate(chunk):
+                    out[idx] = wav[r].clone()
+        return out
+
+    return fn
+
+
+def synthesize_sharded(utterances: list[dict], synth_fn, *, group=None, dst: int | None = 0) -> list | None:
+    """Shard -> synthesise -> host gather.  Every rank passes the same `utterances` list (host data) and its own
+    `synth_fn`; rank r synthesises `shard_utterances(durations, world)[r]`.  Returns the waveforms in list order on
+    rank `dst` (None elsewhere), or on every rank with dst=None.  Without an initialised process group it simply runs
+    everything locally (world size 1)."""
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    mine = shard_utterances([int(u["duration"]) for u in utterances], world)[rank]
+    local = synth_fn([(i, utterances[i]) for i in mine])
+    if set(local) != set(mine):
+        raise RuntimeError(f"rank {rank}: synth_fn returned utterances {sorted(local)} for shard {mine}")
+    if world == 1:
+        return [local[i] for i in range(len(utterances))]
+    if dst is None:
+        parts = [None] * world
+        dist.all_gather_object(parts, local, group=group)
+    else:
+        parts = [None] * world if rank == dst else None
+        dist.gather_object(local, parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    if len(merged) != len(utterances):
+        raise RuntimeError(f"gather returned {len(merged)} of {len(utterances)} utterances")
+    return [merged[i] for i in range(len(utterances))]

@@ -39,6 +39,7 @@ def resample_taps(orig_sr: int, new_sr: int, lowpass_filter_width: int = 6, roll
 _TAPS: dict = {}
 
 
+@nv.on_device
 def resample(wav: torch.Tensor, orig_sr: int, new_sr: int) -> torch.Tensor:
     """wav fp32 [b, n] on the GPU -> [b, ceil(new n / orig)]   (torchaudio.functional.resample, cfm.py:254)."""
     nv.require_device()
@@ -94,6 +95,7 @@ def kaldi_fbank_tables(n_mels: int = 80, sample_rate: int = 16000, n_fft: int = 
 _FBANK: dict = {}
 
 
+@nv.on_device
 def kaldi_fbank_80(wav16k: torch.Tensor) -> torch.Tensor:
     """wav fp32 [b, n] (16 kHz) on the GPU -> fp32 [b, 1 + (n-400)//160, 80]   (extract_fbank_16k)."""
     nv.require_device()
@@ -186,15 +188,18 @@ class PackedEcapa:
         return self._t(w), self._t(b)
 
 
+@nv.on_device
 def ecapa_encode(enc, fbank: torch.Tensor) -> torch.Tensor:
     """ECAPA_TDNN.forward(fbank [b, t, 80], padding_mask=None) on the GPU -> [b, embed_dim]."""
     nv.require_device()
     assert fbank.is_cuda and fbank.dim() == 3
     fbank = fbank.to(f32).contiguous()
     packed = getattr(enc, "_lemas_packed", None)
-    if packed is None or packed.device != fbank.device:
+    key = nv.weights_key(enc)  # replaced / reloaded encoder weights must not meet a stale packed copy
+    if packed is None or packed.device != fbank.device or getattr(enc, "_lemas_packed_key", None) != key:
         packed = PackedEcapa(enc, fbank.device)
         enc._lemas_packed = packed
+        enc._lemas_packed_key = key
     b, t, _ = fbank.shape
     lib = nv.load()
     ws_bytes = lib.lemas_prosody_workspace_bytes(C.byref(packed.w), b, t)

@@ -13,6 +13,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from . import _native as nv
+
 
 class _Block(nn.Module):
     def __init__(self, dim, inter):
@@ -91,7 +93,7 @@ class Vocos(nn.Module):
 
     def engine(self):
         w = self.head.out.weight
-        key = (str(w.device), w._version, w.data_ptr())
+        key = nv.weights_key(self)
         if self._engine is None or self._engine_key != key:
             if w.device.type != "cuda":
                 raise RuntimeError("CUDA error: the lemas_tts B200 build has no CPU path; move the vocoder to a "

@@ -1,8 +1,9 @@
-"""ORACLE helper — imports the *verbatim* reference modules from /root/reference (build container only).
+"""ORACLE helper — imports the *verbatim* reference modules: from /root/reference in the build container, from
+the vendored copy oracle/_ref/ (oracle/make_ref.py; git-ignored, travels with the gpurun snapshot) on the GPU box.
 
-/root/reference does not exist on the GPU box, so nothing in `-m gpu` tests, smoke() or bench.py may
-import this file.  It is used by oracle/gen_golden.py to mint tests/golden/* and by
-oracle/check_against_reference.py.
+Used by oracle/gen_golden*.py to mint tests/golden/* (build container) and by bench.py's CPU legs
+(`--impl reference`, `cpu_baseline`) to time the reference's own CFM.sample.  Never imported by the product or by
+the `-m gpu` tests.
 
 The reference package's __init__ pulls in hydra/soundfile/pydub/..., none of which are installed, so
 a namespace stub for `lemas_tts` is registered whose __path__ points at the reference tree, and the
@@ -21,21 +22,39 @@ from pathlib import Path
 import torch
 
 REFERENCE_ROOT = Path("/root/reference")
+VENDORED_ROOT = Path(__file__).resolve().parent / "_ref"
+
+
+def reference_root() -> Path | None:
+    for root in (REFERENCE_ROOT, VENDORED_ROOT):
+        if (root / "lemas_tts" / "model" / "cfm.py").is_file():
+            return root
+    return None
+
+
+def available() -> bool:
+    return reference_root() is not None
+
 
 
 LAST_T_GRID = None  # the t grid of the most recent odeint call (golden generator reads it)
+LAST_LOOP_SECONDS = None  # wall time of the most recent Euler loop (bench.py scales the loop, not the prologue)
 
 
 def _euler_odeint(func, y0, t, **kwargs):
-    global LAST_T_GRID
+    global LAST_T_GRID, LAST_LOOP_SECONDS
+    import time
+
     assert kwargs.get("method", "euler") == "euler"
     LAST_T_GRID = t.detach().clone()
     ys = [y0]
     y = y0
+    t_start = time.perf_counter()
     for i in range(len(t) - 1):
         t0, t1 = t[i], t[i + 1]
         y = y + (t1 - t0) * func(t0.to(y.dtype), y)
         ys.append(y)
+    LAST_LOOP_SECONDS = time.perf_counter() - t_start
     return torch.stack(ys)
 
 
@@ -69,14 +88,16 @@ def _apply_rotary(t, freqs, scale=1):
 
 def install() -> None:
     """Register stubs; afterwards `from lemas_tts.model.cfm import CFM` loads the reference file."""
-    if not REFERENCE_ROOT.is_dir():
-        raise RuntimeError("/root/reference is only present in the build container")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference sources not found: neither /root/reference nor oracle/_ref "
+                           "(run `python oracle/make_ref.py` in the build container)")
     if "lemas_tts" in sys.modules and getattr(sys.modules["lemas_tts"], "__verbatim__", False):
         return
     for name in [m for m in sys.modules if m == "lemas_tts" or m.startswith("lemas_tts.")]:
         del sys.modules[name]
     pkg = types.ModuleType("lemas_tts")
-    pkg.__path__ = [str(REFERENCE_ROOT / "lemas_tts")]
+    pkg.__path__ = [str(root / "lemas_tts")]
     pkg.__verbatim__ = True
     sys.modules["lemas_tts"] = pkg
 

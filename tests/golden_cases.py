@@ -53,3 +53,36 @@ def prosody_inputs(case: dict):
     noise = syn.synthetic_noise(case["durations"], arch.mel_dim, seed=case["seed"])
     sd = syn.make_dit_state_dict(arch, seed=case["wseed"])
     return arch, audio, text, noise, sd
+
+
+# ----------------------------------------------------------------------------------- full-size, full-NFE goldens
+_MF = GOLDEN / "MANIFEST_full.json"
+FULL_CASES = json.loads(_MF.read_text())["cases"] if _MF.exists() else {}
+
+
+def full_inputs(case: dict) -> dict:
+    """Same derivation as oracle/gen_golden_full.py:full_inputs (checked through `in_sums`)."""
+    import dataclasses
+
+    if case["kind"] == "c3":
+        arch = dataclasses.replace(syn.FULL_ARCH, use_prosody_encoder=True)
+        b = syn.c3_batch(32, seed=case["seed"])
+        idx = torch.tensor(case["pick"])
+        lens, dur = b["lens"][idx], b["duration"][idx]
+        text = b["text"][idx]
+        text = text[:, : int((text >= 0).sum(1).max())]
+        cond = b["audio"][idx]
+        noise = syn.synthetic_noise(dur.tolist(), arch.mel_dim, seed=case["seed"])
+        return dict(arch=arch, cond=cond, text=text, lens=lens, duration=dur, noise=noise, edit_mask=None,
+                    durations=dur.tolist())
+    arch = syn.FULL_ARCH
+    B, Tc, N = case["batch"], case["ref_frames"], case["frames"]
+    cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
+    text = syn.synthetic_text_ids(B, case["n_text"], arch.text_num_embeds, seed=case["seed"])
+    noise = syn.synthetic_noise([N] * B, arch.mel_dim, seed=case["seed"])
+    edit_mask = None
+    if case.get("edit"):
+        edit_mask = torch.ones(B, Tc, dtype=torch.bool)
+        edit_mask[:, case["edit"][0]: case["edit"][1]] = False
+    return dict(arch=arch, cond=cond, text=text, lens=None, duration=case.get("duration", N), noise=noise,
+                edit_mask=edit_mask, durations=[N] * B)
