@@ -41,9 +41,6 @@ constexpr int B5_QF = 0, B5_QE = 2, B5_KF = 4, B5_KE = B5_KF + A5_STAGES, B5_VF 
 static_assert(B5_COUNT * 8 + 8 <= 512, "barrier block");
 
 constexpr float A5_RESCALE_LOG2 = 8.0f;
-#ifndef A5_DEPHASE_CLK
-#define A5_DEPHASE_CLK 600   // head start of key half A over key half B at the start of an item
-#endif
 
 struct A5Item {
   int b, h, q0, kvl, n_blocks;
@@ -64,7 +61,10 @@ DEVI A5Item a5_item(const AttnParams& p, int it) {
   return w;
 }
 
-template <uint32_t kPolyMask>
+// kCtrlLast: the four control warps take the HIGHEST warp indices (the softmax warps are warps 0-15) instead of the
+// lowest — the issue arbiter of a sub-partition is not age-neutral, and the MMA issuer's few instructions are the
+// latency-critical ones.
+template <uint32_t kPolyMask, bool kCtrlLast>
 __global__ void __launch_bounds__(A5_THREADS, 1)
 attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
                   const __grid_constant__ AttnParams p) {
@@ -73,6 +73,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B5_COUNT);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int ctrl = kCtrlLast ? warp - 16 : warp;   // 0 TMA, 1 / 2 MMA issuer of tile 0 / 1, 3 idle; < 0 or > 3: softmax
+  const int sw = kCtrlLast ? warp : warp - 4;      // softmax warp index 0..15 (warp % 4 == sw % 4 either way)
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -99,7 +101,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (ctrl == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,7 +112,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
   const int n_items = p.n_items;
   const int stride = gridDim.x;
 
-  if (warp == 0) {
+  if (ctrl == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int qn = 0, r = 0;
@@ -140,9 +142,9 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
         ++qn;
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (ctrl == 1 || ctrl == 2) {
     // ------------------------------------------------------------------ MMA issuer of tile t
-    const int t = warp - 1;
+    const int t = ctrl - 1;
     constexpr uint32_t idesc = umma_idesc_f16(128, 64);   // both MMA shapes are M128 N64 K16
     const uint32_t tmem_s = tmem_base + t * 256;          // + 64 * half
     const uint32_t tmem_o = tmem_s + 128;                 // + 64 * half
@@ -189,10 +191,14 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       ATT_WAIT_P(bars + B5_QF + slot, (qn >> 1) & 1, 6, it);
       ATT_WAIT_P(bars + B5_KF + r % A5_STAGES, (r / A5_STAGES) & 1, 4, 0);
       tc_fence_after();
+      if (t == 1 && p.dephase_tile > 0 && nb > 2) {  // tile 1 starts a fraction of a block period behind tile 0
+        const long long t_go = clock64() + p.dephase_tile;
+        while (clock64() < t_go) { }
+      }
       if (elect_one()) issue_s(0, r);
       __syncwarp();
-      if (A5_DEPHASE_CLK > 0 && nb > 2) {  // head start for key half A (the two warps of a sub-partition and tile
-        const long long t_go = clock64() + A5_DEPHASE_CLK;  // should not be in their exponential phase together)
+      if (p.dephase_half > 0 && nb > 2) {  // head start for key half A (the two warps of a sub-partition and tile
+        const long long t_go = clock64() + p.dephase_half;  // should not be in their exponential phase together)
         while (clock64() < t_go) { }
       }
       if (elect_one()) issue_s(1, r);
@@ -207,6 +213,10 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           ATT_WAIT_P(p_full + x, (g + j) & 1, 7 + x, j);
+#ifdef LEMAS_ATT_TRACE
+          if (p.trace && lane == 0 && it == (int)blockIdx.x && j < 32 && (long long)blockIdx.x == p.trace[7])
+            p.trace[4096 + ((t * 32 + j) * 2 + x) * 2] = clock64();
+#endif
           // the first P V of an item overwrites O: the merge of the previous item must have read it
           if (j == 0 && x == 0) ATT_WAIT_P(bars + B5_OE + t, (on & 1) ^ 1, 9, it);
           tc_fence_after();
@@ -223,6 +233,10 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
               issue_s(x, rr + 1);  // overwrites P_x(j): executes behind the P V just issued
             }
           }
+#ifdef LEMAS_ATT_TRACE
+          if (p.trace && lane == 0 && it == (int)blockIdx.x && j < 32 && (long long)blockIdx.x == p.trace[7])
+            p.trace[4096 + ((t * 32 + j) * 2 + x) * 2 + 1] = clock64();
+#endif
           __syncwarp();
         }
       }
@@ -231,9 +245,8 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
       ++on;
       ++qn;
     }
-  } else if (warp >= 4) {
+  } else if (sw >= 0 && sw < 16) {
     // ------------------------------------------------------------------ softmax warps
-    const int sw = warp - 4;
     const int t = sw >> 3;
     const int half = (sw >> 2) & 1;
     const int sub = warp & 3;          // TMEM sub-partition: lanes [32*sub, 32*sub+32)
@@ -429,7 +442,7 @@ attention5_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (ctrl == 1) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace lemas
@@ -454,20 +467,22 @@ int attention_variant() {
   return env >= 0 ? env : kDefaultVariant;
 }
 
-template <uint32_t kPolyMask>
+template <uint32_t kPolyMask, bool kCtrlLast>
 int launch_v5(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, void* stream) {
   static unsigned long long configured = 0;
-  LEMAS_CUDA_OK(ensure_dynamic_smem(attention5_kernel<kPolyMask>, A5_SMEM, configured));
+  LEMAS_CUDA_OK(ensure_dynamic_smem(attention5_kernel<kPolyMask, kCtrlLast>, A5_SMEM, configured));
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  LEMAS_CUDA_OK(launch_pdl(attention5_kernel<kPolyMask>, dim3(grid), dim3(A5_THREADS), A5_SMEM, (cudaStream_t)stream,
+  LEMAS_CUDA_OK(launch_pdl(attention5_kernel<kPolyMask, kCtrlLast>, dim3(grid), dim3(A5_THREADS), A5_SMEM, (cudaStream_t)stream,
                            tmQK, tmVT, p));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
 }  // namespace
 
-// variants: 0 = v3 (attention.cu); 1.. = v5 with the share of key pairs whose exp2 runs on the FMA pipe:
-// 1: 1/4, 2: 3/8, 3: 1/2, 4: none
+// variants: 0 = v3 (attention.cu); v5: 1 = control warps first, 1/4 of the exp2 on the FMA pipe; 2 = control warps
+// last, 1/4; 3 = control warps last, all exp2 on the SFU.  LEMAS_A5_DEPHASE_HALF / LEMAS_A5_DEPHASE_TILE (clocks)
+// override the pipeline stagger (experiments).  v6 (attention6.cu): 4 = all exp2 on the SFU, 5 = 1/4 on the FMA pipe,
+// 6 = 3/8.
 extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                                    void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
   LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
@@ -499,10 +514,23 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   p.inner = inner;
   p.n_pairs = (seq + 255) / 256;
   p.n_items = p.n_pairs * heads * batch;
+  static int dephase_half = -1, dephase_tile = -1;
+  if (dephase_half < 0) {
+    const char* e = getenv("LEMAS_A5_DEPHASE_HALF");
+    dephase_half = e ? atoi(e) : (variant >= 4 ? 400 : 600);
+    e = getenv("LEMAS_A5_DEPHASE_TILE");
+    dephase_tile = e ? atoi(e) : 300;
+  }
+  p.dephase_half = dephase_half;
+  p.dephase_tile = dephase_tile;
+  if (variant >= 4) {  // v6 (attention6.cu): one tile per item, double-buffered scores
+    p.n_pairs = (seq + 127) / 128;
+    p.n_items = p.n_pairs * heads * batch;
+    return attention_v6_launch(tmQK, tmVT, p, variant - 4, stream);
+  }
   switch (variant) {
-    case 2: return launch_v5<0x29292929u>(tmQK, tmVT, p, stream);
-    case 3: return launch_v5<0x55555555u>(tmQK, tmVT, p, stream);
-    case 4: return launch_v5<0u>(tmQK, tmVT, p, stream);
-    default: return launch_v5<0x11111111u>(tmQK, tmVT, p, stream);
+    case 2: return launch_v5<0x11111111u, true>(tmQK, tmVT, p, stream);
+    case 3: return launch_v5<0u, true>(tmQK, tmVT, p, stream);
+    default: return launch_v5<0x11111111u, false>(tmQK, tmVT, p, stream);
   }
 }

@@ -37,6 +37,23 @@ __global__ void __launch_bounds__(512, 1) k(const float* in, uint32_t* out, long
       const float mx = fmaxf(fmax3f(m4[0], m4[1], m4[2]), m4[3]);
       if (__any_sync(0xffffffffu, (mx - mc) * c > 8.f)) mc = mx;
     }
+    if (VAR == 5 || VAR == 7) {  // max pass: FMNMX3, 4 chains (the kernels' current form)
+      float m4[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], s[i], s[32 + i]);
+      const float mx = fmaxf(fmax3f(m4[0], m4[1], m4[2]), m4[3]);
+      if (__any_sync(0xffffffffu, (mx - mc) * c > 8.f)) mc = mx;
+    }
+    if (VAR == 6 || VAR == 8) {  // max pass: 2-input FMNMX, 8 chains
+      float m8[8] = {-1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+      for (int i = 0; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], s[i]);
+      const float mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+      if (__any_sync(0xffffffffu, (mx - mc) * c > 8.f)) mc = mx;
+    }
+    if (VAR == 5 || VAR == 6) {
+      for (int i = 0; i < 32; ++i) pk[i] = __float_as_uint(s[i]) ^ __float_as_uint(mc);
+    }
     if (VAR == 0 || VAR == 3) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -61,7 +78,7 @@ __global__ void __launch_bounds__(512, 1) k(const float* in, uint32_t* out, long
           pk[q] = pack(e[2 * q], e[2 * q + 1]);
         }
       }
-    } else if (VAR == 4) {
+    } else if (VAR == 4 || VAR == 7 || VAR == 8) {
       // DEPTH of every 4 key pairs get their exp2 from the FMA/ALU pipes (Cody-Waite + degree-3 polynomial)
       const uint64_t magic2 = f32x2(12582912.f, 12582912.f), nmagic2 = f32x2(-12582912.f, -12582912.f);
       const uint64_t k3 = f32x2(0.0555041f, 0.0555041f), k2 = f32x2(0.2402265f, 0.2402265f),
@@ -151,6 +168,11 @@ int main() {
   run<3, 0>("max pass + vote + kernel order", in, out, clk);
   run<4, 1>("1 of 4 pairs on the FMA pipe (poly3)", in, out, clk);
   run<4, 2>("2 of 4 pairs on the FMA pipe (poly3)", in, out, clk);
+  run<5, 0>("max pass only: FMNMX3 x32, 4 chains", in, out, clk);
+  run<6, 0>("max pass only: FMNMX x64, 8 chains", in, out, clk);
+  run<7, 1>("FMNMX3 max + 1/4 poly (v6 body)", in, out, clk);
+  run<8, 1>("FMNMX 8-chain max + 1/4 poly", in, out, clk);
+  run<8, 2>("FMNMX 8-chain max + 2/4 poly", in, out, clk);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return 0;
