@@ -12,10 +12,12 @@ struct AttnParams {
   const int* kv_len;
   __half* out;
   int seq, heads, inner;
+  int debug;          // timing experiments (LEMAS_A7_DEBUG): skip parts of the MMA issuers' work
   int dephase_half, dephase_tile;   // v5 only: pipeline stagger in clocks (see attention5.cu)
   int n_pairs, n_items;   // v5 only: query-tile pairs per (batch, head); work items = n_pairs * heads * batch
 };
 
+int attention_v7_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, int poly, void* stream);
 int attention_v6_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, int poly, void* stream);
 int attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                         void* out16, int32_t batch, int32_t seq, int32_t heads, long long* trace, void* stream);

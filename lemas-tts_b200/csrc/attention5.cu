@@ -456,7 +456,7 @@ extern "C" void lemas_debug_attention_trace(void* buf) { g_att_trace = static_ca
 extern "C" void lemas_debug_attention_variant(int v) { g_att_variant = v; }
 
 namespace {
-constexpr int kDefaultVariant = 1;
+constexpr int kDefaultVariant = 0;   // v3 (attention.cu) is the fastest measured kernel (C2: 59 us; v5 63, v6 / v7 71)
 int attention_variant() {
   if (g_att_variant >= 0) return g_att_variant;
   static int env = -2;
@@ -482,7 +482,7 @@ int launch_v5(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams
 // variants: 0 = v3 (attention.cu); v5: 1 = control warps first, 1/4 of the exp2 on the FMA pipe; 2 = control warps
 // last, 1/4; 3 = control warps last, all exp2 on the SFU.  LEMAS_A5_DEPHASE_HALF / LEMAS_A5_DEPHASE_TILE (clocks)
 // override the pipeline stagger (experiments).  v6 (attention6.cu): 4 = all exp2 on the SFU, 5 = 1/4 on the FMA pipe,
-// 6 = 3/8.
+// 6 = 3/8.  v7 (attention7.cu, four key parts): 7 = all on the SFU, 8 = 1/4 on the FMA pipe, 9 = 3/8.
 extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                                    void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
   LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
@@ -521,11 +521,15 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
     e = getenv("LEMAS_A5_DEPHASE_TILE");
     dephase_tile = e ? atoi(e) : 300;
   }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("LEMAS_A7_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
   p.dephase_half = dephase_half;
   p.dephase_tile = dephase_tile;
-  if (variant >= 4) {  // v6 (attention6.cu): one tile per item, double-buffered scores
+  if (variant >= 4) {  // v6 / v7 (attention6.cu / attention7.cu): one tile per item, double-buffered scores
     p.n_pairs = (seq + 127) / 128;
     p.n_items = p.n_pairs * heads * batch;
+    if (variant >= 7) return attention_v7_launch(tmQK, tmVT, p, variant - 7, stream);
     return attention_v6_launch(tmQK, tmVT, p, variant - 4, stream);
   }
   switch (variant) {

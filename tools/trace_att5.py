@@ -16,7 +16,7 @@ LIB = PKG / "lib" / "liblemas_b200_trace.so"
 
 
 def build():
-    srcs = ["common.cu", "attention.cu", "attention5.cu", "attention6.cu"]
+    srcs = ["common.cu", "attention.cu", "attention5.cu", "attention6.cu", "attention7.cu"]
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-DLEMAS_ATT_TRACE", "-shared", "-o", str(LIB), *[str(PKG / "csrc" / s) for s in srcs],
            "-lcuda"]
@@ -70,9 +70,22 @@ def main():
         d = (st[:, 1:] - st[:, :-1]).double()
         per = (tw[1:, 0] - tw[:-1, 0]).double()
         sl = slice(3, nb - 1)
-        print(f"{w:2d} {w >> 3:4d} {(w >> 2) & 1:4d} {w & 3:3d} | " + " | ".join(f"{d[sl, i].mean().item():8.0f}" for i in range(5))
+        print(f"{w:2d} {w >> 3:4d} {(w >> 2) & (3 if variant >= 7 else 1):4d} {w & 3:3d} | " + " | ".join(f"{d[sl, i].mean().item():8.0f}" for i in range(5))
               + f" | {per[3:nb - 2].mean().item():7.0f} | {(tw[0, 1] - t0).item():6d}")
     print("item span (first stamp -> last P stored):", (t[:, nb - 1, 6].max() - t0).item(), "clk")
+    if variant >= 7:
+        ss = trace[4096:4096 + 128].view(32, 4).cpu().double()[:nb]
+        ps = trace[4096 + 128:4096 + 256].view(32, 4).cpu().double()[:nb]
+        sl = slice(3, nb - 1)
+        print("S issuer: wait k_full %.0f | wait pv_done x4 %.0f | issue + commits %.0f | period %.0f" % (
+            (ss[sl, 1] - ss[sl, 0]).mean(), (ss[sl, 2] - ss[sl, 1]).mean(), (ss[sl, 3] - ss[sl, 2]).mean(),
+            (ss[1:, 0] - ss[:-1, 0])[3:nb - 2].mean()))
+        print("P V issuer 0: wait v_full %.0f | wait p_full %.0f | issue + commits %.0f | period %.0f" % (
+            (ps[sl, 1] - ps[sl, 0]).mean(), (ps[sl, 2] - ps[sl, 1]).mean(), (ps[sl, 3] - ps[sl, 2]).mean(),
+            (ps[1:, 0] - ps[:-1, 0])[3:nb - 2].mean()))
+        print("S issue start of block g relative to P V issuer 0 done with block g-2:",
+              [int(x) for x in (ss[2:nb, 2] - ps[:nb - 2, 3])[:12].tolist()])
+        return
     if variant >= 4:  # v6: P V issuers; stamps per (block, half): P observed, P V issued
         mm = trace[4096:4096 + 128].view(32, 2, 2).cpu().double()[:nb]
         for x in range(2):
