@@ -51,6 +51,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU utterance batch (C4: default 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--all-rows", action="store_true",
+                    help="C3 (ragged batch): also compute the padded rows that cannot reach a valid row (reference-"
+                         "identical padding; default: skip them, lemas_sample_args.flags)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the sharded C4 block (256 utterances over the ranks)")
     return ap.parse_args()
 
 
@@ -385,6 +389,7 @@ def run_b200(args):
     model = CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"), **pros)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
+    model.skip_padded_rows = wl.name == "C3" and not args.all_rows
     voc = Vocos()
     voc.load_state_dict(vsd, strict=True)
     voc = voc.to(dev).eval()
@@ -465,6 +470,43 @@ def run_b200(args):
     eng.profile(False)
     prof_ms = e0.elapsed_time(e1)
 
+    # BASELINE.json configs[3]: 256 utterances (256 reference + 512 generated frames) dealt to the ranks by
+    # shard_utterances and synthesised in batches of 32 through lemas_tts.parallel (strong scaling: the list is fixed,
+    # the ranks share it).  Device time of each rank's shard (CFM.sample + Vocos.decode + D2H of the waveforms), max
+    # over ranks; the host-side gather of the waveforms follows outside the timed region.
+    c4 = None
+    if args.workload == "C2" and not args.no_c4:
+        from lemas_tts.parallel import make_synth_fn, shard_utterances, synthesize_sharded
+
+        c4cfg = syn.CONFIGS["C4"]
+        n_utt = c4cfg.batch
+        cond4 = syn.synthetic_ref_mel(n_utt, c4cfg.ref_frames, arch.mel_dim, seed=c4cfg.seed)
+        text4 = syn.synthetic_text_ids(n_utt, c4cfg.n_text, arch.text_num_embeds, seed=c4cfg.seed)
+        utts = [dict(cond=cond4[i], text=text4[i], duration=c4cfg.total_frames) for i in range(n_utt)]
+        fn = make_synth_fn(model, voc, steps=c4cfg.steps, cfg_strength=c4cfg.cfg_strength,
+                           sway_sampling_coef=c4cfg.sway_coef, seed=c4cfg.seed, batch_size=32)
+        mine = shard_utterances([u["duration"] for u in utts], world)[rank]
+        fn([(i, utts[i]) for i in mine[:32]])  # warm-up: one batch (graph capture, workspace growth)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        local = fn([(i, utts[i]) for i in mine])
+        e1.record()
+        e1.synchronize()
+        ms_c4 = e0.elapsed_time(e1)
+        if world > 1:
+            ms_c4 = max_over_ranks(ms_c4, device=dev)
+        wavs = synthesize_sharded(utts, lambda items: {i: local[i] for i, _ in items}, dst=0)  # host gather only
+        gen = n_utt * (c4cfg.total_frames - c4cfg.ref_frames)
+        if rank == 0:
+            assert len(wavs) == n_utt and all(w.numel() == (c4cfg.total_frames - c4cfg.ref_frames - 1) * HOP for w in wavs)
+            c4 = {"workload": f"C4: {n_utt} utterances (ref {c4cfg.ref_frames} frames, N {c4cfg.total_frames}, "
+                              f"{c4cfg.n_text} phones, NFE {c4cfg.steps}) sharded over {world} rank(s), batches of 32",
+                  "scaling": "strong", "seconds": ms_c4 * 1e-3, "value": gen / (ms_c4 * 1e-3), "unit": UNIT,
+                  "utterances_per_rank": len(mine), "x_realtime": (gen * HOP / SR) / (ms_c4 * 1e-3)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -510,6 +552,8 @@ def run_b200(args):
         "dtype": "f16", "data": "synthetic",
         "rtf": sec_step / (frames * HOP / SR), "x_realtime": (frames * HOP / SR) / sec_step,
         "config": {"workload": wl.describe(),
+                   "padded_rows": ("skipped beyond the influence cone of the position-embedding convolutions (valid rows "
+                                   "unchanged, tests/test_fullnfe_gpu.py)" if model.skip_padded_rows else "computed"),
                    "weights": "full 336M-parameter DiT (22 layers) + Vocos, seeded random init (no checkpoints offline)",
                    "step": f"CFM.sample ({variants * cfg.steps} co-batched DiT forwards, graph-replayed ODE steps) + "
                            "Vocos.decode of one utterance batch per GPU",
@@ -529,6 +573,8 @@ def run_b200(args):
         "kernels": kinds, "profiled_step_ms": prof_ms,
         "clocks": clocks,
     }
+    if c4 is not None:
+        line["c4_sharded"] = c4
     if world == 1 and not args.no_cpu_baseline:
         info = cpu_reference_sample(wl, euler_steps=2)
         line["cpu_baseline"] = {"value": info["frames"] / info["seconds"], "unit": UNIT, "cores": info["cores"],

@@ -85,6 +85,9 @@ typedef struct lemas_gemm_desc {
   int32_t inner;             /* heads*64: columns [0,inner)=q, [inner,2*inner)=k, rest=v                        */
   void* vt; int32_t vt_ld;   /* V transposed out: fp16 [b, head, 64, vt_ld]                                     */
   int32_t max_ctas;          /* 0 = one persistent CTA per SM                                                   */
+  const int32_t* row_limit;  /* optional, device int32 [sequences]: 256-row tiles that start at or beyond row_limit[b]
+                                of their sequence are not computed at all (ragged batches, see lemas_sample_args.flags);
+                                honoured by the CTA-pair kernel (block_n 256), NULL = every row                       */
 } lemas_gemm_desc;
 
 int lemas_gemm_f16(const lemas_gemm_desc* d, void* stream);
@@ -93,6 +96,9 @@ int lemas_gemm_f16(const lemas_gemm_desc* d, void* stream);
  * x: fp32 [rows, dim]; scale/shift: fp32 [dim] (+ b*mod_bstride, b = row / seq_len). */
 int lemas_ln_modulate(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
                       int32_t rows, int32_t dim, int32_t seq_len, void* stream);
+/* Same, skipping rows whose position inside their sequence is >= row_limit[row / seq_len] (device int32, may be NULL). */
+int lemas_ln_modulate_rows(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
+                           int32_t rows, int32_t dim, int32_t seq_len, const int32_t* row_limit, void* stream);
 
 /* LayerNorm with affine weight/bias, fp32 in -> fp16 and/or fp32 out (vocos backbone norms). */
 int lemas_ln_affine(const float* x, const float* weight, const float* bias, void* out16, float* out32,
@@ -198,8 +204,15 @@ typedef struct lemas_sample_args {
   void* workspace; int64_t workspace_bytes;
   int32_t use_graph;          /* 1: capture ONE ODE step into a CUDA graph (cached per shape/workspace in the engine)
                                  and replay it for every step; step-dependent values are read from device memory.
-                                 Ignored (eager launches) when a trajectory is requested or profiling is on.      */
+                                 Ignored (eager launches) when profiling is on.                                   */
+  int32_t flags;              /* LEMAS_SAMPLE_SKIP_PADDED_ROWS: ragged batches (kv_len != NULL) — the transformer blocks
+                                 of Euler step s only compute rows r < kv_len[b] + 30 (steps-1-s), rounded up to 128:
+                                 the two k=31 convolutions of the position embedding (dit.py:97-98) are the only path
+                                 from a padded row to a valid one, 30 rows per step, so rows beyond that cone can never
+                                 reach a valid row of the result.  Valid rows (r < kv_len[b]) are unchanged; padded rows
+                                 of the returned state then differ from the reference's (callers slice them off).     */
 } lemas_sample_args;
+#define LEMAS_SAMPLE_SKIP_PADDED_ROWS 1
 
 /* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */
 int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream);

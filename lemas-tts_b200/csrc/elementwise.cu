@@ -15,11 +15,16 @@ constexpr int LN_MAX_VEC = 8;
 template <bool AFFINE>
 __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, const float* __restrict__ p0, const float* __restrict__ p1, int mod_bstride,
-          __half* __restrict__ out16, float* __restrict__ out32, int rows, int dim, int seq_len, float eps) {
+          __half* __restrict__ out16, float* __restrict__ out32, int rows, int dim, int seq_len, float eps,
+          const int* __restrict__ row_limit) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (row_limit != nullptr) {  // ragged batches: rows beyond the sequence's limit are not needed (lemas_sample_args.flags)
+    const int b = row / seq_len;
+    if (row - b * seq_len >= __ldg(row_limit + b)) return;
+  }
   const int lane = threadIdx.x & 31;
   const int nvec = dim >> 7;
   const float4* xr = reinterpret_cast<const float4*>(x + (long)row * dim);
@@ -222,9 +227,18 @@ __global__ void cfg_euler_dev_kernel(const float* __restrict__ pred, int ld_pred
 __global__ void __launch_bounds__(1024)
 step_begin_kernel(const float* __restrict__ mod_table, long mod_w, float* __restrict__ mod_cur,
                   const float* __restrict__ t_grid, int* __restrict__ step_ctr, float* __restrict__ state,
-                  float cfg_strength) {
+                  float cfg_strength, int* __restrict__ row_limit, const int* __restrict__ kv_len2, int n_seq, int seq,
+                  int steps) {
   const int step = *step_ctr;
   __syncthreads();  // everyone has read the counter before thread 0 advances it
+  // Ragged batches (LEMAS_SAMPLE_SKIP_PADDED_ROWS): rows of sequence b that can still reach one of its valid rows
+  // before the last step — 30 rows per remaining step through the two k=31 convolutions of the position embedding
+  // (dit.py:97-98) — rounded up to the 128-key attention block so that every key row a valid query can read is fresh.
+  if (row_limit != nullptr)
+    for (int b = threadIdx.x; b < n_seq; b += blockDim.x) {
+      const int need = kv_len2[b] + 30 * (steps - 1 - step);
+      row_limit[b] = min(seq, (need + 127) / 128 * 128);
+    }
   const float4* src = reinterpret_cast<const float4*>(mod_table + (long)step * mod_w);
   float4* dst = reinterpret_cast<float4*>(mod_cur);
   for (long i = threadIdx.x; i < mod_w / 4; i += blockDim.x) dst[i] = src[i];
@@ -239,8 +253,10 @@ step_begin_kernel(const float* __restrict__ mod_table, long mod_w, float* __rest
 }
 
 int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const float* t_grid, int* step_ctr,
-                      float* state, float cfg_strength, cudaStream_t st) {
-  step_begin_kernel<<<1, 1024, 0, st>>>(mod_table, mod_w, mod_cur, t_grid, step_ctr, state, cfg_strength);
+                      float* state, float cfg_strength, int* row_limit, const int* kv_len2, int n_seq, int seq, int steps,
+                      cudaStream_t st) {
+  step_begin_kernel<<<1, 1024, 0, st>>>(mod_table, mod_w, mod_cur, t_grid, step_ctr, state, cfg_strength, row_limit,
+                                        kv_len2, n_seq, seq, steps);
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }
@@ -390,21 +406,27 @@ using namespace lemas;
 
 extern "C" {
 
-int lemas_ln_modulate(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
-                      int32_t rows, int32_t dim, int32_t seq_len, void* stream) {
+int lemas_ln_modulate_rows(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
+                           int32_t rows, int32_t dim, int32_t seq_len, const int32_t* row_limit, void* stream) {
   LEMAS_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_VEC, "lemas_ln_modulate: dim must be a multiple of 128, <= 1024");
   LEMAS_REQUIRE(rows > 0 && seq_len > 0, "lemas_ln_modulate: bad shape");
   LEMAS_CUDA_OK(launch_pdl(ln_kernel<false>, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, x, scale, shift,
-                           mod_bstride, (__half*)out16, (float*)nullptr, rows, dim, seq_len, 1e-6f));
+                           mod_bstride, (__half*)out16, (float*)nullptr, rows, dim, seq_len, 1e-6f,
+                           (const int*)row_limit));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
+}
+
+int lemas_ln_modulate(const float* x, const float* scale, const float* shift, int32_t mod_bstride, void* out16,
+                      int32_t rows, int32_t dim, int32_t seq_len, void* stream) {
+  return lemas_ln_modulate_rows(x, scale, shift, mod_bstride, out16, rows, dim, seq_len, nullptr, stream);
 }
 
 int lemas_ln_affine(const float* x, const float* weight, const float* bias, void* out16, float* out32, int32_t rows,
                     int32_t dim, float eps, void* stream) {
   LEMAS_REQUIRE(dim % 128 == 0 && dim <= 128 * LN_MAX_VEC, "lemas_ln_affine: dim must be a multiple of 128, <= 1024");
   ln_kernel<true><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, weight, bias, 0, (__half*)out16, out32, rows,
-                                                                    dim, 1 << 30, eps);
+                                                                    dim, 1 << 30, eps, nullptr);
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

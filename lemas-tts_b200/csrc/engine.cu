@@ -10,7 +10,8 @@ namespace lemas {
 
 int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream);
 int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const float* t_grid, int* step_ctr,
-                      float* state, float cfg_strength, cudaStream_t st);
+                      float* state, float cfg_strength, int* row_limit, const int* kv_len2, int n_seq, int seq, int steps,
+                      cudaStream_t st);
 int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
                          long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st);
 
@@ -30,7 +31,7 @@ struct Carver {
 struct DitBuffers {
   __half *x16, *ct16, *h0_16, *c1_16, *a16, *o16, *qk16, *vt16, *ff16;
   float *inv_embed, *h0, *x, *pred, *t_dev, *sinus, *t1, *temb, *mod, *mod_cur, *state, *y_state;
-  int *kv_len2, *step_ctr;
+  int *kv_len2, *step_ctr, *row_limit;
   int npad;
   int64_t bytes;
 };
@@ -60,6 +61,7 @@ static DitBuffers carve(const lemas_dit_config& c, int batch, int seq, int steps
   b.temb = cv.take<float>((int64_t)steps * D);
   b.mod = cv.take<float>((int64_t)steps * ((int64_t)c.depth * 6 * D + 2 * D));
   b.kv_len2 = cv.take<int>(2 * batch);
+  b.row_limit = cv.take<int>(2 * batch);
   b.mod_cur = cv.take<float>((int64_t)c.depth * 6 * D + 2 * D);
   b.state = cv.take<float>(4);
   b.step_ctr = cv.take<int>(1);
@@ -84,7 +86,7 @@ struct lemas_engine {
   // One captured ODE step per (shape, workspace) — replayed `steps` times; everything step-dependent is read from
   // device memory (step_begin_kernel), so the same executable graph serves every step and every later call.
   struct StepGraph {
-    int batch, seq, steps, variants, has_kv;   // steps: the workspace carve-up (hence every captured pointer) depends on it
+    int batch, seq, steps, variants, has_kv, flags;   // steps: the workspace carve-up (hence every captured pointer) depends on it
     float cfg;
     const void *ws, *rope, *traj;
     cudaGraphExec_t exec;
@@ -182,7 +184,7 @@ static lemas_gemm_desc base_desc(const void* a, int batches, int rows, int lda, 
 
 // One DiT forward on `variants*batch` co-batched sequences; mod = this step's modulation row.
 static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, int seq, int variants, const float* mod,
-                       const int* kv_len2, const float* rope, float* pred, cudaStream_t st) {
+                       const int* kv_len2, const float* rope, float* pred, const int* row_limit, cudaStream_t st) {
   const lemas_dit_config& c = e->cfg;
   const lemas_dit_weights& w = e->w;
   const int D = c.dim, inner = c.heads * 64, F = c.dim * c.ff_mult;
@@ -212,11 +214,12 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
   for (int l = 0; l < c.depth; ++l) {
     const lemas_dit_layer& L = w.layers[l];
     const float* m = mod + (int64_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, m + D, m, 0, b.a16, M, D, seq, st)); }
+    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + D, m, 0, b.a16, M, D, seq, row_limit, st)); }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_qkv, 3 * inner, D, 3 * inner, seq, LEMAS_EPI_QKV_ROPE, 256);
       d.bias = L.b_qkv; d.out16 = b.qk16; d.ld16 = 2 * inner; d.rope = rope;
       d.rope_cols = c.rope_heads * 64; d.inner = inner; d.vt = b.vt16; d.vt_ld = b.npad;
+      d.row_limit = row_limit;
       PROF(LEMAS_PROF_GEMM_QKV);
       LEMAS_TRY(gemm_launch(d, st));
     }
@@ -228,25 +231,28 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
       lemas_gemm_desc d = base_desc(b.o16, 1, M, inner, L.w_out, D, inner, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
       d.bias = L.b_out; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 2 * D; d.gate_bstride = 0;
       d.row_valid = kv_len2;
+      d.row_limit = row_limit;
       PROF(LEMAS_PROF_GEMM_OUT);
       LEMAS_TRY(gemm_launch(d, st));
     }
-    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, st)); }
+    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, row_limit, st)); }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_ff1, F, D, F, seq, LEMAS_EPI_GELU_TANH_F16, 256);
       d.bias = L.b_ff1; d.out16 = b.ff16; d.ld16 = F;
+      d.row_limit = row_limit;
       PROF(LEMAS_PROF_GEMM_FF1);
       LEMAS_TRY(gemm_launch(d, st));
     }
     {
       lemas_gemm_desc d = base_desc(b.ff16, 1, M, F, L.w_ff2, D, F, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
       d.bias = L.b_ff2; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 5 * D; d.gate_bstride = 0;
+      d.row_limit = row_limit;
       PROF(LEMAS_PROF_GEMM_FF2);
       LEMAS_TRY(gemm_launch(d, st));
     }
   }
   const float* mf = mod + (int64_t)c.depth * 6 * D;  // modules.py:333: (scale, shift)
-  { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate(b.x, mf, mf + D, 0, b.a16, M, D, seq, st)); }
+  { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate_rows(b.x, mf, mf + D, 0, b.a16, M, D, seq, row_limit, st)); }
   {
     lemas_gemm_desc d = base_desc(b.a16, 1, M, D, w.w_proj, 128, D, c.mel_dim, seq, LEMAS_EPI_BIAS_F32, 128);
     d.bias = w.b_proj; d.out32 = pred; d.ld32 = 128;
@@ -308,14 +314,16 @@ extern "C" {
 static int ode_step(lemas_engine* e, const DitBuffers& b, const lemas_sample_args* a, int variants, const int* kv2,
                     float* y, cudaStream_t st) {
   const lemas_dit_config& c = e->cfg;
+  int* row_limit = (kv2 != nullptr && (a->flags & LEMAS_SAMPLE_SKIP_PADDED_ROWS)) ? b.row_limit : nullptr;
   const int rows = a->batch * a->seq;
   const int64_t mod_w = (int64_t)c.depth * 6 * c.dim + 2 * c.dim;
   {
     PROF(LEMAS_PROF_CFG_EULER);
     LEMAS_TRY(step_begin_launch(b.mod, mod_w, b.mod_cur, b.t_dev, b.step_ctr, b.state,
-                                variants == 2 ? a->cfg_strength : 0.f, st));
+                                variants == 2 ? a->cfg_strength : 0.f, row_limit, kv2, variants * a->batch, a->seq,
+                                a->steps, st));
   }
-  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, st));
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, row_limit, st));
   PROF(LEMAS_PROF_CFG_EULER);
   LEMAS_TRY(cfg_euler_dev_launch(b.pred, 128, y, b.x16, 128, variants, a->trajectory, (long)rows * c.mel_dim, rows,
                                  c.mel_dim, b.state, variants == 2 ? 1 : 0, st));
@@ -353,7 +361,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   lemas_engine::StepGraph* g = nullptr;
   for (auto& cand : e->graphs)
     if (cand.batch == a->batch && cand.seq == a->seq && cand.steps == a->steps && cand.variants == variants &&
-        cand.has_kv == (kv2 != nullptr) &&
+        cand.has_kv == (kv2 != nullptr) && cand.flags == a->flags &&
         cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope &&
         cand.traj == a->trajectory)
       g = &cand;
@@ -380,7 +388,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
       cudaGraphExecDestroy(e->graphs.front().exec);
       e->graphs.erase(e->graphs.begin());
     }
-    e->graphs.push_back({a->batch, a->seq, a->steps, variants, kv2 != nullptr, a->cfg_strength, a->workspace, a->rope,
+    e->graphs.push_back({a->batch, a->seq, a->steps, variants, kv2 != nullptr, a->flags, a->cfg_strength, a->workspace, a->rope,
                          a->trajectory, exec, nodes});
     g = &e->graphs.back();
   }
@@ -399,7 +407,7 @@ int lemas_dit_forward(lemas_engine* e, const lemas_sample_args* a, float t, floa
   LEMAS_TRY(check_args(e, a, 1, &b));
   LEMAS_REQUIRE(pred && a->text_uncond, "lemas_dit_forward: pred and text_uncond are required");
   LEMAS_TRY(prepare(e, b, a, 2, 1, &t, st));
-  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, 2, b.mod, a->kv_len ? b.kv_len2 : nullptr, a->rope, pred, st));
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, 2, b.mod, a->kv_len ? b.kv_len2 : nullptr, a->rope, pred, nullptr, st));
   if (hidden_out)
     LEMAS_CUDA_OK(cudaMemcpyAsync(hidden_out, b.x, sizeof(float) * 2LL * a->batch * a->seq * e->cfg.dim,
                                   cudaMemcpyDeviceToDevice, st));

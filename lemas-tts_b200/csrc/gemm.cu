@@ -349,7 +349,7 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   p.out32 = d.out32; p.ld32 = d.ld32;
   p.resid = d.resid; p.ldr = d.ldr;
   p.gate = d.gate; p.gate_bstride = d.gate_bstride;
-  p.row_valid = d.row_valid; p.seq_len = d.seq_len;
+  p.row_valid = d.row_valid; p.seq_len = d.seq_len; p.row_limit = d.row_limit;
   p.rope = reinterpret_cast<const float2*>(d.rope); p.rope_cols = d.rope_cols; p.inner = d.inner;
   p.vt = static_cast<__half*>(d.vt); p.vt_ld = d.vt_ld;
 

@@ -172,6 +172,12 @@ DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], c
   __syncwarp();  // the staging buffer is rewritten by the next block
 }
 
+// Ragged batches: a 256-row pair tile that starts at or beyond its sequence's row limit is skipped by every role
+// (producer, MMA issuer, epilogue evaluate the same predicate, so ring / accumulator phases stay in step).
+DEVI bool tile_skipped(const GemmParams& p, int batch_item, int first_row) {
+  return p.row_limit != nullptr && first_row >= __ldg(p.row_limit + batch_item);
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -222,6 +228,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_idx = tile % n_tiles;
         const int mt = tile / n_tiles;
         const int bi = mt / m_tiles_b;
+        if (tile_skipped(p, bi, (mt - bi * m_tiles_b) * (2 * G2_BM))) continue;
         const int m0 = (mt - bi * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM;
         const int n0 = n_idx * G2_BN + (int)rank * (G2_BN / 2);
         for (int it = 0; it < p.k_iters; ++it) {
@@ -243,6 +250,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        {
+          const int mt = tile / n_tiles, bi = mt / m_tiles_b;
+          if (tile_skipped(p, bi, (mt - bi * m_tiles_b) * (2 * G2_BM))) continue;
+        }
         mbar_wait_cluster(acc_empty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
@@ -277,6 +288,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int mt = tile / n_tiles;
       RowCtx rc;
       rc.b = mt / m_tiles_b;
+      if (tile_skipped(p, rc.b, (mt - rc.b * m_tiles_b) * (2 * G2_BM))) continue;
       rc.pos0 = (mt - rc.b * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM + sub * 32;
       rc.nrows = min(32, p.rows - rc.pos0);
       rc.grow0 = (long)rc.b * p.rows + rc.pos0;

@@ -14,6 +14,7 @@ struct GemmParams {
   const float* resid; int ldr;
   const float* gate; int gate_bstride;
   const int* row_valid;
+  const int* row_limit;   // gemm2 only: tiles starting at or beyond row_limit[batch item] are skipped
   int seq_len;
   const float2* rope; int rope_cols; int inner;
   __half* vt; int vt_ld;

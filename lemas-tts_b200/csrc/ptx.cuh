@@ -44,6 +44,14 @@ DEVI void mbar_arrive(uint64_t* bar) {
 #ifndef LEMAS_MBAR_TIMEOUT_CLK
 #define LEMAS_MBAR_TIMEOUT_CLK 4000000000ll
 #endif
+// Back-off between failed polls (ns; 0 = poll as fast as try_wait returns): a spinning warp competes for the issue
+// slots of the warps that share its SM sub-partition.
+#ifndef LEMAS_MBAR_SLEEP_NS
+#define LEMAS_MBAR_SLEEP_NS 0
+#endif
+DEVI void mbar_backoff() {
+  if (LEMAS_MBAR_SLEEP_NS > 0) asm volatile("nanosleep.u32 %0;" ::"n"(LEMAS_MBAR_SLEEP_NS));
+}
 DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   long long t0 = 0;
@@ -55,6 +63,7 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     if (ok) return;
+    mbar_backoff();
     if ((++spins & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -316,6 +325,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok) : "r"(bar_addr), "r"(parity) : "memory");
     if (ok) return;
+    mbar_backoff();
     if ((++spins & 255u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;

@@ -19,6 +19,7 @@ _lib = None
 
 EPI_BIAS_F16, EPI_QKV_ROPE, EPI_GELU_TANH_F16, EPI_GELU_ERF_F16, EPI_GATE_RESID_F32 = 0, 1, 2, 3, 4
 EPI_BIAS_F32, EPI_ADD_F32_F16, EPI_MISH_F16, EPI_MISH_RESID_F32 = 5, 6, 7, 8
+SAMPLE_SKIP_PADDED_ROWS = 1
 PROF_KINDS = ["preloop", "in_proj", "conv_pos", "ln_mod", "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
               "proj_out", "cfg_euler"]
 
@@ -34,7 +35,7 @@ class GemmDesc(C.Structure):
         ("out16", vp), ("ld16", i32), ("out32", vp), ("ld32", i32),
         ("resid", vp), ("ldr", i32), ("gate", vp), ("gate_bstride", i32),
         ("row_valid", vp), ("seq_len", i32), ("rope", vp), ("rope_cols", i32), ("inner", i32),
-        ("vt", vp), ("vt_ld", i32), ("max_ctas", i32),
+        ("vt", vp), ("vt_ld", i32), ("max_ctas", i32), ("row_limit", vp),
     ]
 
 
@@ -59,7 +60,7 @@ class SampleArgs(C.Structure):
     _fields_ = [("batch", i32), ("seq", i32), ("steps", i32), ("t_grid_host", C.POINTER(f32)),
                 ("cfg_strength", f32), ("y", vp), ("step_cond", vp), ("text_cond", vp), ("text_uncond", vp),
                 ("kv_len", vp), ("rope", vp), ("trajectory", vp), ("workspace", vp), ("workspace_bytes", i64),
-                ("use_graph", i32)]
+                ("use_graph", i32), ("flags", i32)]
 
 
 class VocosLayer(C.Structure):
@@ -113,6 +114,7 @@ SIGNATURES = {
     "lemas_engine_profile_read": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(i64), vp]),
     "lemas_gemm_f16": (C.c_int, [C.POINTER(GemmDesc), vp]),
     "lemas_ln_modulate": (C.c_int, [vp, vp, vp, i32, vp, i32, i32, i32, vp]),
+    "lemas_ln_modulate_rows": (C.c_int, [vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]),
     "lemas_ln_affine": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32, vp]),
     "lemas_attention_f16": (C.c_int, [vp, i32, vp, i32, vp, vp, i32, i32, i32, vp]),
     "lemas_skinny_linear_f32": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -92,6 +92,12 @@ class CFM(nn.Module):
         self.sigma = sigma
         self.odeint_kwargs = odeint_kwargs
         self.vocab_char_map = vocab_char_map
+        # Ragged batches (B > 1, cfm.py:336-339): skip the transformer-block rows that can never reach a valid row
+        # (lemas_sample_args.flags, include/lemas_b200.h).  Valid rows of `out` are unchanged; PADDED rows then differ
+        # from the reference's leaky values, so it is opt-in (LEMAS_SKIP_PADDED_ROWS=1 or set the attribute).
+        import os
+
+        self.skip_padded_rows = os.environ.get("LEMAS_SKIP_PADDED_ROWS", "0") == "1"
         self.use_prosody_encoder = bool(use_prosody_encoder and prosody_cfg_path and prosody_ckpt_path)
         if self.use_prosody_encoder:
             from .backbones.prosody_encoder import ProsodyEncoder
@@ -242,7 +248,7 @@ class CFM(nn.Module):
         if return_trajectory:
             traj = torch.empty(steps + 1, batch, max_duration, self.num_channels, device=device, dtype=torch.float32)
         engine.sample_loop(y, step_cond, text_c, text_u if cfg_strength >= 1e-5 else None, t, cfg_strength,
-                           kv_len=kv_len, trajectory=traj)
+                           kv_len=kv_len, trajectory=traj, skip_padded_rows=self.skip_padded_rows and not duplicate_test)
         tr.clear_cache()
 
         out = torch.where(cond_mask, cond, y)

@@ -3,7 +3,7 @@
     python oracle/make_ref.py            (build container only: reads /root/reference, which the GPU box does not have)
 
 The reference is pure Python and cannot be pip-installed offline (no setup.py / pyproject.toml, >= 20 absent
-dependencies — DESIGN.md §2).  Its hot path, however, lives in six self-contained files; this recipe copies them,
+dependencies — DESIGN.md §2).  Its hot path, however, lives in six self-contained files; this recipe copies them (and the two CLI scripts),
 byte for byte, to oracle/_ref/lemas_tts/model/... together with a MANIFEST (source path + sha256).  oracle/_ref/ is
 git-ignored (reference sources never enter the history) but NOT gpurun-ignored, so it travels with the snapshot like a
 built .so.  oracle/verbatim.py imports the files from /root/reference when that exists and from oracle/_ref/ otherwise;
@@ -21,7 +21,10 @@ from pathlib import Path
 SRC = Path("/root/reference/lemas_tts")
 DST = Path(__file__).resolve().parent / "_ref" / "lemas_tts"
 FILES = ["model/cfm.py", "model/modules.py", "model/utils.py", "model/backbones/dit.py",
-         "model/backbones/prosody_encoder.py", "model/backbones/ecapa_tdnn.py"]
+         "model/backbones/prosody_encoder.py", "model/backbones/ecapa_tdnn.py",
+         # the two command-line entry points, executed UNCHANGED against this repo's package by
+         # tests/test_reference_scripts_gpu.py
+         "scripts/tts_multilingual.py", "scripts/speech_edit_multilingual.py"]
 
 
 def make(verbose: bool = True) -> bool:

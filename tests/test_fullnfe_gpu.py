@@ -73,7 +73,10 @@ def test_full_nfe_matches_reference(full_model, name, trajectory):
         assert torch.equal(out.cpu()[0, : keep.numel()][keep], inp["cond"][0][keep])
 
 
-def test_full_nfe_c3_slice_ragged_prosody(tmp_path):
+@pytest.mark.parametrize("skip_rows", [False, True])
+def test_full_nfe_c3_slice_ragged_prosody(tmp_path, skip_rows):
+    """skip_rows=True: the influence-cone row skipping (LEMAS_SAMPLE_SKIP_PADDED_ROWS) must leave every VALID row
+    within the same bar of the reference and change nothing but padded rows w.r.t. the full computation."""
     from lemas_tts.model.backbones.dit import DiT
     from lemas_tts.model.cfm import CFM
 
@@ -88,10 +91,17 @@ def test_full_nfe_c3_slice_ragged_prosody(tmp_path):
                syn.make_prosody_state_dict(syn.PROSODY_CFG, case["pseed"]).items()})
     model.load_state_dict(sd, strict=True)
     model = model.cuda()
-    out, _ = model.sample(cond=inp["cond"].cuda(), text=inp["text"].cuda(), duration=inp["duration"].cuda(),
-                          lens=inp["lens"].cuda(), steps=case["steps"], cfg_strength=case["cfg"],
-                          sway_sampling_coef=case["sway"], noise=inp["noise"], use_acc_grl=False,
-                          use_prosody_encoder=True, return_trajectory=False)
+    kw = dict(cond=inp["cond"].cuda(), text=inp["text"].cuda(), duration=inp["duration"].cuda(),
+              lens=inp["lens"].cuda(), steps=case["steps"], cfg_strength=case["cfg"], sway_sampling_coef=case["sway"],
+              noise=inp["noise"], use_acc_grl=False, use_prosody_encoder=True, return_trajectory=False)
+    model.skip_padded_rows = skip_rows
+    out, _ = model.sample(**kw)
     durs = torch.tensor(inp["durations"])
     valid = torch.arange(int(durs.max()))[None] < durs[:, None]
-    _check(out.cpu()[valid], gold["out"][valid], f"full_C3_b4 valid rows (32 steps, durations {inp['durations']})")
+    _check(out.cpu()[valid], gold["out"][valid],
+           f"full_C3_b4 valid rows (32 steps, durations {inp['durations']}, skip_padded_rows={skip_rows})")
+    if skip_rows:
+        model.skip_padded_rows = False
+        full, _ = model.sample(**kw)
+        assert torch.equal(out.cpu()[valid], full.cpu()[valid]), "row skipping changed a valid row"
+        assert not torch.equal(out.cpu()[~valid], full.cpu()[~valid]), "nothing was skipped?"

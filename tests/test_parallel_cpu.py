@@ -52,3 +52,65 @@ def test_broadcast_and_sharding_two_ranks(tmp_path):
     a = torch.load(tmp_path / "shard0.pt")
     b = torch.load(tmp_path / "shard1.pt")
     assert sorted(a + b) == [0, 1, 2, 3] and a and b
+
+
+# ------------------------------------------------------------------------------- sharded synthesis (host logic)
+def _fake_synth(items):
+    """Stand-in for make_synth_fn(model, vocoder): a waveform that depends on the utterance only."""
+    out = {}
+    for idx, u in items:
+        n = (int(u["duration"]) - int(u["cond"].shape[0]) - 1) * 4
+        out[idx] = torch.full((n,), float(idx)) + u["text"].float().sum() * 1e-3
+    return out
+
+
+def _utterances():
+    g = torch.Generator().manual_seed(0)
+    durs = [700, 300, 300, 512, 900, 300, 512, 128]
+    return [dict(cond=torch.randn(d // 3, 100, generator=g), text=torch.randint(0, 50, (d // 10,), generator=g), duration=d)
+            for d in durs]
+
+
+def test_synthesize_sharded_single_process_runs_everything_locally():
+    from lemas_tts.parallel import synthesize_sharded
+
+    utts = _utterances()
+    wavs = synthesize_sharded(utts, _fake_synth)
+    want = _fake_synth(list(enumerate(utts)))
+    assert len(wavs) == len(utts) and all(torch.equal(wavs[i], want[i]) for i in range(len(utts)))
+
+
+def _shard_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lemas_tts.parallel import shard_utterances, synthesize_sharded
+
+        utts = _utterances()
+        seen = []
+
+        def synth(items):
+            seen.extend(i for i, _ in items)
+            return _fake_synth(items)
+
+        got = synthesize_sharded(utts, synth, dst=0)
+        assert sorted(seen) == shard_utterances([u["duration"] for u in utts], world)[rank]
+        assert (got is None) == (rank != 0)
+        everywhere = synthesize_sharded(utts, _fake_synth, dst=None)
+        assert len(everywhere) == len(utts)
+        if rank == 0:
+            torch.save(dict(got=got, everywhere=everywhere), os.path.join(tmp, "gathered.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_synthesize_sharded_two_ranks_gathers_in_list_order(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = torch.load(tmp_path / "gathered.pt")
+    utts = _utterances()
+    want = _fake_synth(list(enumerate(utts)))
+    for key in ("got", "everywhere"):
+        assert len(res[key]) == len(utts)
+        for i in range(len(utts)):
+            assert torch.equal(res[key][i], want[i]), (key, i)
