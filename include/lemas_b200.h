@@ -217,8 +217,11 @@ typedef struct lemas_sample_args {
 /* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */
 int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream);
 
-/* Per-kernel-kind device timing of the sampler (measurement aid, off by default).  When enabled every launch issued
- * by lemas_sampler_run / lemas_dit_forward is bracketed by CUDA events on the launching stream.
+/* Per-kernel-kind device timing of the sampler (measurement aid, off by default).  enable = 1: every launch issued
+ * by lemas_sampler_run / lemas_dit_forward is bracketed by CUDA events on the launching stream (eager launches);
+ * enable = 2: lemas_sampler_run records the event pairs INSIDE the captured ODE-step graph and reads them back after
+ * every replay, i.e. per-kernel times of the graph-replayed step the production path runs (the pre-loop kernels and
+ * step 0 are not included); enable = 0: off.
  * lemas_engine_profile_read synchronises the stream, adds the elapsed times since the last read to ms[kind] and
  * launches[kind] (arrays of LEMAS_PROF_KINDS entries) and clears the record. */
 enum lemas_prof_kind {

@@ -1,5 +1,5 @@
 // Helpers shared by the attention kernels (attention.cu: v3, one 128-query tile per CTA, two CTAs per SM;
-// attention5.cu: v5, persistent CTA with two query tiles): packed fp32 arithmetic, MUFU, the TS-form MMA and the
+// attention7.cu: v7, persistent CTA with double-buffered scores): packed fp32 arithmetic, MUFU, the TS-form MMA and the
 // hang-hunting waits.
 #pragma once
 #include "common.h"
@@ -13,12 +13,11 @@ struct AttnParams {
   __half* out;
   int seq, heads, inner;
   int debug;          // timing experiments (LEMAS_A7_DEBUG): skip parts of the MMA issuers' work
-  int dephase_half, dephase_tile;   // v5 only: pipeline stagger in clocks (see attention5.cu)
-  int n_pairs, n_items;   // v5 only: query-tile pairs per (batch, head); work items = n_pairs * heads * batch
+  int dephase_half, dephase_tile;   // v7 only: start-up stagger of the key parts in clocks
+  int n_pairs, n_items;   // v7 only: 128-query tiles per (batch, head); work items = n_pairs * heads * batch
 };
 
 int attention_v7_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, int poly, void* stream);
-int attention_v6_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, int poly, void* stream);
 int attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                         void* out16, int32_t batch, int32_t seq, int32_t heads, long long* trace, void* stream);
 

@@ -398,8 +398,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
 
 using namespace lemas;
 
-// v3 launcher (one 128-query tile per CTA, two CTAs per SM).  The public entry point lemas_attention_f16 lives in
-// attention5.cu and dispatches between this kernel and the persistent two-tile kernel.
+// v3 launcher (one 128-query tile per CTA, two CTAs per SM); lemas_attention_f16 below dispatches.
 int lemas::attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                                void* out16, int32_t batch, int32_t seq, int32_t heads, long long* trace, void* stream) {
   const int inner = heads * ATT_D;
@@ -429,4 +428,72 @@ int lemas::attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, in
   LEMAS_CUDA_OK(launch_pdl(attention_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, (cudaStream_t)stream, tmQK, tmVT, p));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
+}
+
+static long long* g_att_trace = nullptr;
+static int g_att_variant = -1;   // -1: default (LEMAS_ATT_VARIANT or built-in choice)
+// debug aids (not part of the public header)
+extern "C" void lemas_debug_attention_trace(void* buf) { g_att_trace = static_cast<long long*>(buf); }
+extern "C" void lemas_debug_attention_variant(int v) { g_att_variant = v; }
+
+namespace {
+constexpr int kDefaultVariant = 0;   // v3 is the fastest measured kernel (C2: 59 us; v5 63, v6 / v7 71 us)
+int attention_variant() {
+  if (g_att_variant >= 0) return g_att_variant;
+  static int env = -2;
+  if (env == -2) {
+    const char* e = getenv("LEMAS_ATT_VARIANT");
+    env = e ? atoi(e) : -1;
+  }
+  return env >= 0 ? env : kDefaultVariant;
+}
+
+}  // namespace
+
+// LEMAS_ATT_VARIANT / lemas_debug_attention_variant: 0 = v3 (this file, production); 7 / 8 / 9 = v7 (attention7.cu,
+// experimental: persistent CTA, double-buffered scores, four key parts) with 0, 1/4, 3/8 of the exp2 on the FMA pipe;
+// 18-21 = v7 timing ablations (wrong results).  LEMAS_A7_DEPHASE (clocks) sets v7's start-up stagger.
+extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
+                                   void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
+  LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
+  LEMAS_REQUIRE(ld_qk % 8 == 0 && vt_ld % 8 == 0 && vt_ld >= seq, "lemas_attention_f16: ld_qk/vt_ld must be multiples of 8");
+  LEMAS_REQUIRE(batch >= 1 && seq >= 1 && heads >= 1, "lemas_attention_f16: bad shape");
+  const int variant = attention_variant();
+  if (variant < 7)
+    return attention_v3_launch(qk, ld_qk, vt, vt_ld, kv_len, out16, batch, seq, heads, g_att_trace, stream);
+  const int inner = heads * 64;
+  CUtensorMap tmQK, tmVT;
+  {
+    uint64_t dims[3] = {(uint64_t)2 * inner, (uint64_t)seq, (uint64_t)batch};
+    uint64_t strides[2] = {(uint64_t)ld_qk * 2, (uint64_t)seq * ld_qk * 2};
+    uint32_t box[3] = {64, 128, 1};
+    LEMAS_TRY(make_tensor_map_f16(&tmQK, qk, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)seq, 64, (uint64_t)batch * heads};
+    uint64_t strides[2] = {(uint64_t)vt_ld * 2, (uint64_t)64 * vt_ld * 2};
+    uint32_t box[3] = {64, 64, 1};
+    LEMAS_TRY(make_tensor_map_f16(&tmVT, vt, 3, dims, strides, box));
+  }
+  AttnParams p = {};
+  p.trace = g_att_trace;
+  p.kv_len = kv_len;
+  p.out = static_cast<__half*>(out16);
+  p.seq = seq;
+  p.heads = heads;
+  p.inner = inner;
+  static int dephase_half = -1, dephase_tile = -1;
+  if (dephase_half < 0) {
+    const char* e = getenv("LEMAS_A7_DEPHASE");
+    dephase_half = e ? atoi(e) : 150;
+    dephase_tile = 0;
+  }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("LEMAS_A7_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
+  p.dephase_half = dephase_half;
+  p.dephase_tile = dephase_tile;
+  p.n_pairs = (seq + 127) / 128;   // 128-query tiles per (batch, head)
+  p.n_items = p.n_pairs * heads * batch;
+  return attention_v7_launch(tmQK, tmVT, p, variant - 7, stream);
 }

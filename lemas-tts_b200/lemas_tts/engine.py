@@ -205,8 +205,9 @@ class DiTEngine:
             trajectory.copy_(stage)
         return y
 
-    def profile(self, enable: bool) -> None:
-        """Bracket every sampler launch with CUDA events (measurement aid, see lemas_engine_profile)."""
+    def profile(self, enable) -> None:
+        """Measurement aid (lemas_engine_profile): 1 / True = CUDA events around every eager launch, 2 = events inside
+        the replayed step graph (per-kernel times of the production path), 0 / False = off."""
         nv.check(nv.load().lemas_engine_profile(self._handle, int(enable)))
 
     @nv.on_device

@@ -16,7 +16,7 @@ LIB = PKG / "lib" / "liblemas_b200_trace.so"
 
 
 def build():
-    srcs = ["common.cu", "attention.cu", "attention5.cu", "attention6.cu", "attention7.cu"]
+    srcs = ["common.cu", "attention.cu", "attention7.cu"]
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-DLEMAS_ATT_TRACE", "-shared", "-o", str(LIB), *[str(PKG / "csrc" / s) for s in srcs],
            "-lcuda"]
