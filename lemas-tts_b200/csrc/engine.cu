@@ -110,7 +110,7 @@ static const char* const kProfNames[LEMAS_PROF_KINDS] = {
     "K8 FF1 GEMM + GELU", "K8 FF2 GEMM + gate + residual", "K13 proj_out", "K13-K15 CFG + clamp + Euler"};
 
 struct ProfScope {
-  lemas_engine* e; cudaStream_t st; ProfRecord r; bool on; bool range;
+  lemas_engine* e; cudaStream_t st; ProfRecord r; bool on; bool range; unsigned ext = 0;
   ProfScope(const lemas_engine* ce, int kind, cudaStream_t s)
       : e(const_cast<lemas_engine*>(ce)), st(s), on(ce->profile != 0), range(ce->nvtx) {
     if (range) nvtxRangePushA(kProfNames[kind]);
@@ -118,10 +118,15 @@ struct ProfScope {
     auto get = [&]() { cudaEvent_t ev; if (!e->free_events.empty()) { ev = e->free_events.back(); e->free_events.pop_back(); }
                        else cudaEventCreate(&ev); return ev; };
     r.kind = kind; r.e0 = get(); r.e1 = get();
-    cudaEventRecord(r.e0, st);
+    // inside a stream capture a plain record is only an internal dependency; an EXTERNAL record becomes an event-record
+    // node whose timestamp can be read after the graph has run (graph-profile mode)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    ext = cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+    cudaEventRecordWithFlags(r.e0, st, ext);
   }
   ~ProfScope() {
-    if (on) { cudaEventRecord(r.e1, st); e->records.push_back(r); }
+    if (on) { cudaEventRecordWithFlags(r.e1, st, ext); e->records.push_back(r); }
     if (range) nvtxRangePop();
   }
 };
@@ -413,6 +418,8 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
         if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.kind >= 0 && r.kind < LEMAS_PROF_KINDS) {
           e->acc_ms[r.kind] += t;
           e->acc_n[r.kind] += 1;
+        } else {
+          (void)cudaGetLastError();   // never leave a sticky error behind a measurement aid
         }
       }
     }
