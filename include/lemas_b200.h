@@ -293,6 +293,23 @@ int lemas_text_embedding(const lemas_text_weights* w, const int32_t* ids, const 
                          int32_t seq, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Waveform-side pre / post-processing of infer_batch_process on the device.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t lemas_audio_prep_workspace_bytes(int64_t samples);
+/* utils_infer.py:487-493: wav fp32 [channels, samples] (channel stride ch_stride elements) -> mono fp32 [samples]
+ * (mean over channels), stats[0] = rms = sqrt(mean(mono^2)), stats[1] = target_rms, and mono = mono * target_rms / rms
+ * when rms < target_rms.  The 24 kHz resampling that follows is lemas_resample_sinc.  No host synchronisation. */
+int lemas_audio_prep(const float* wav, int32_t channels, int64_t samples, int64_t ch_stride, float target_rms,
+                     float* mono, float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+/* utils_infer.py:552-553: wav = wav * rms / target_rms in place when rms < target_rms (stats from lemas_audio_prep). */
+int lemas_audio_unscale(float* wav, int64_t samples, const float* stats, void* stream);
+/* utils_infer.py:581-622, one step of the chunk loop: out (fp64 [na + nb - fade]) = a[: na - fade] ++ (a[na - fade :] *
+ * linspace(1, 0, fade) + b[: fade] * linspace(0, 1, fade)) ++ b[fade :], evaluated like numpy's float64 arithmetic,
+ * then clipped to [-clip, clip] when clip > 0.  na == 0: out = (double) b (the first chunk).  a: fp64, b: fp32. */
+int lemas_audio_crossfade(const double* a, int64_t na, const float* b, int64_t nb, int64_t fade, double* out, double clip,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Prosody path of the prosody-conditioned model, once per utterance (cfm.py:248-262): 24 kHz -> 16 kHz resampling,
  * kaldi fbank, Pretssel ECAPA-TDNN (prosody_encoder.py:30-334).  fp32 throughout; activations channels-last.
  * ---------------------------------------------------------------------------------------------------------- */

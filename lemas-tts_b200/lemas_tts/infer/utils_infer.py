@@ -373,14 +373,26 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
     """utils_infer.py:464-625 (generator).  Non-streaming: yields (final_wave, 24000, combined_spectrogram) once;
     streaming: yields (chunk, 24000) pieces of `chunk_size` samples."""
     audio, sr = ref_audio
-    if audio.shape[0] > 1:
-        audio = torch.mean(audio, dim=0, keepdim=True)
-    rms = torch.sqrt(torch.mean(torch.square(audio)))
-    if rms < target_rms:
-        audio = audio * target_rms / rms
-    if sr != target_sample_rate:
-        audio = torchaudio.transforms.Resample(sr, target_sample_rate)(audio)
-    audio = audio.to(device)
+    # On a CUDA device the waveform-side arithmetic runs in csrc/audio.cu / csrc/prosody.cu (mono mix, RMS scaling,
+    # sinc resampling, un-scaling, cross-fade, clip): the raw reference audio goes up once, the final waveform comes
+    # down once, nothing in between synchronises with the host.
+    on_device = torch.device(device if device is not None else "cpu").type == "cuda"
+    stats = None
+    if on_device:
+        from lemas_tts import audio_native, prosody_native
+
+        audio, stats = audio_native.prep_reference_audio(audio.to(device), target_rms)
+        if sr != target_sample_rate:
+            audio = prosody_native.resample(audio, sr, target_sample_rate)
+    else:
+        if audio.shape[0] > 1:
+            audio = torch.mean(audio, dim=0, keepdim=True)
+        rms = torch.sqrt(torch.mean(torch.square(audio)))
+        if rms < target_rms:
+            audio = audio * target_rms / rms
+        if sr != target_sample_rate:
+            audio = torchaudio.transforms.Resample(sr, target_sample_rate)(audio)
+        audio = audio.to(device)
 
     if type(ref_text) == str and len(ref_text[-1].encode("utf-8")) == 1:
         ref_text = ref_text + " "
@@ -413,9 +425,14 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
                 wave = vocoder.decode(generated)
             else:
                 wave = vocoder(generated)
-            if rms < target_rms:
-                wave = wave * rms / target_rms
-            wave = wave.squeeze().cpu().numpy()
+            if on_device:
+                wave = audio_native.unscale_(wave.contiguous(), stats).squeeze()
+                if streaming:
+                    wave = wave.cpu().numpy()
+            else:
+                if rms < target_rms:
+                    wave = wave * rms / target_rms
+                wave = wave.squeeze().cpu().numpy()
             if streaming:
                 for j in range(0, len(wave), chunk_size):
                     yield wave[j:j + chunk_size], target_sample_rate
@@ -437,7 +454,10 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
         waves.append(wave)
         specs.append(spec)
     if waves:
-        final_wave = np.clip(cross_fade_concat(waves, cross_fade_duration), -0.999, 0.999)
+        if on_device:
+            final_wave = audio_native.cross_fade_concat(waves, cross_fade_duration, target_sample_rate, clip=0.999)
+        else:
+            final_wave = np.clip(cross_fade_concat(waves, cross_fade_duration), -0.999, 0.999)
         yield final_wave, target_sample_rate, np.concatenate(specs, axis=1)
     else:
         yield None, target_sample_rate, None
