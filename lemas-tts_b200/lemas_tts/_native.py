@@ -236,3 +236,20 @@ def weights_key(module) -> tuple:
         n += 1
         dev = t.device
     return (str(dev), n, ver, ptrs)
+
+
+def state_fingerprint(sd: dict) -> str:
+    """Content fingerprint of a state dict (names, shapes, dtypes, fp64 sum and a strided sample sum of every tensor):
+    the file name of the packed-weight blob that belongs to these weights (LEMAS_PACKED_CACHE)."""
+    import hashlib
+
+    h = hashlib.sha1()
+    sums = []
+    for k in sorted(sd):
+        v = sd[k]
+        h.update(f"{k}|{tuple(v.shape)}|{v.dtype}|".encode())
+        f = v.detach().reshape(-1)
+        sums.append(torch.stack((f.double().sum(), f[:: 997].double().sum())))
+    if sums:
+        h.update(torch.stack(sums).cpu().numpy().tobytes())
+    return h.hexdigest()[:20]

@@ -34,9 +34,13 @@ def _dev(t: torch.Tensor, device, dtype) -> torch.Tensor:
 class DiTEngine:
     """Owns the packed DiT weights on one device and a native engine handle."""
 
-    def __init__(self, sd: dict, *, dim: int, depth: int, heads: int, ff_mult: int, text_dim: int, mel_dim: int,
+    BLOB_VERSION = 1
+
+    def __init__(self, sd: dict | None, *, dim: int, depth: int, heads: int, ff_mult: int, text_dim: int, mel_dim: int,
                  pe_attn_head: int | None = None, qk_norm: str | None = None, device="cuda",
-                 prefix: str = "transformer."):
+                 prefix: str = "transformer.", packed: dict | None = None):
+        """`sd`: state dict in the reference key layout (packed here: fp16 K-major GEMM operands, concatenated QKV /
+        AdaLN matrices, tap-major conv weights), or `packed`: the tensors a previous `export_blob` wrote."""
         nv.require_device()
         if qk_norm is not None:
             raise RuntimeError("lemas_b200 error: qk_norm is not supported by the sm_100a engine "
@@ -46,73 +50,90 @@ class DiTEngine:
         self.text_dim, self.mel_dim = text_dim, mel_dim
         self.inner = heads * 64
         self.rope_heads = heads if pe_attn_head is None else int(pe_attn_head)
+        self.pe_attn_head = pe_attn_head
         D, M, Dt, dv = dim, mel_dim, text_dim, self.device
         p = prefix
-        keep = self._keep = []  # every tensor the native side holds a pointer to
+        self._packed = {}  # name -> tensor: everything the native side holds a pointer to (also what export_blob writes)
 
-        def hold(t):
-            keep.append(t)
-            return t
+        def take(name, make):
+            t = packed[name].to(dv) if packed is not None else make()
+            self._packed[name] = t
+            return nv.ptr(t)
 
         w = nv.DitWeights()
-        w.time_w0 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.0.weight"], dv, f32)))
-        w.time_b0 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.0.bias"], dv, f32)))
-        w.time_w2 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.2.weight"], dv, f32)))
-        w.time_b2 = nv.ptr(hold(_dev(sd[p + "time_embed.time_mlp.2.bias"], dv, f32)))
-        ada_w = [sd[f"{p}transformer_blocks.{i}.attn_norm.linear.weight"] for i in range(depth)]
-        ada_b = [sd[f"{p}transformer_blocks.{i}.attn_norm.linear.bias"] for i in range(depth)]
-        ada_w.append(sd[p + "norm_out.linear.weight"])
-        ada_b.append(sd[p + "norm_out.linear.bias"])
-        w.adaln_w = nv.ptr(hold(_dev(torch.cat([t.float() for t in ada_w], 0), dv, f32)))
-        w.adaln_b = nv.ptr(hold(_dev(torch.cat([t.float() for t in ada_b], 0), dv, f32)))
+        w.time_w0 = take("time_w0", lambda: _dev(sd[p + "time_embed.time_mlp.0.weight"], dv, f32))
+        w.time_b0 = take("time_b0", lambda: _dev(sd[p + "time_embed.time_mlp.0.bias"], dv, f32))
+        w.time_w2 = take("time_w2", lambda: _dev(sd[p + "time_embed.time_mlp.2.weight"], dv, f32))
+        w.time_b2 = take("time_b2", lambda: _dev(sd[p + "time_embed.time_mlp.2.bias"], dv, f32))
 
-        proj = sd[p + "input_embed.proj.weight"].float()  # [D, 2*mel + text_dim]: columns x | cond | text
-        assert proj.shape == (D, 2 * M + Dt), proj.shape
+        def adaln(kind):
+            parts = [sd[f"{p}transformer_blocks.{i}.attn_norm.linear.{kind}"] for i in range(depth)]
+            parts.append(sd[p + f"norm_out.linear.{kind}"])
+            return _dev(torch.cat([t.float() for t in parts], 0), dv, f32)
+
+        w.adaln_w = take("adaln_w", lambda: adaln("weight"))
+        w.adaln_b = take("adaln_b", lambda: adaln("bias"))
+
         self.ct_ld = (M + Dt + 63) // 64 * 64
-        w_x = torch.zeros(D, 128)
-        w_x[:, :M] = proj[:, :M]
-        w_ct = torch.zeros(D, self.ct_ld)
-        w_ct[:, : M + Dt] = proj[:, M:]
-        w.w_in_x = nv.ptr(hold(_dev(w_x, dv, f16)))
-        w.w_in_ct = nv.ptr(hold(_dev(w_ct, dv, f16)))
-        w.b_in = nv.ptr(hold(_dev(sd[p + "input_embed.proj.bias"], dv, f32)))
+
+        def in_proj(which):  # input_embed.proj.weight [D, 2*mel + text_dim]: columns x | cond | text
+            proj = sd[p + "input_embed.proj.weight"].float()
+            assert proj.shape == (D, 2 * M + Dt), proj.shape
+            if which == "x":
+                w_x = torch.zeros(D, 128)
+                w_x[:, :M] = proj[:, :M]
+                return _dev(w_x, dv, f16)
+            w_ct = torch.zeros(D, self.ct_ld)
+            w_ct[:, : M + Dt] = proj[:, M:]
+            return _dev(w_ct, dv, f16)
+
+        w.w_in_x = take("w_in_x", lambda: in_proj("x"))
+        w.w_in_ct = take("w_in_ct", lambda: in_proj("ct"))
+        w.b_in = take("b_in", lambda: _dev(sd[p + "input_embed.proj.bias"], dv, f32))
         w.ct_ld = self.ct_ld
 
         groups = 16
         gc = D // groups
         w.conv_dense = 0 if gc == 64 else 1
-        for j, idx in enumerate((0, 2)):
+
+        def conv_weight(idx):
             cw = sd[f"{p}input_embed.conv_pos_embed.conv1d.{idx}.weight"].float()  # [D, D/16, 31]
             taps = cw.shape[-1]
             assert cw.shape == (D, gc, 31), cw.shape
             if gc == 64:
-                packed = cw.permute(2, 0, 1).reshape(taps * D, gc)
-            else:  # block-diagonal dense: out channel o reads input channels of its own group only
-                dense = torch.zeros(taps, D, D)
-                for g in range(groups):
-                    dense[:, g * gc:(g + 1) * gc, g * gc:(g + 1) * gc] = cw[g * gc:(g + 1) * gc].permute(2, 0, 1)
-                packed = dense.reshape(taps * D, D)
-            w.conv_w[j] = nv.ptr(hold(_dev(packed, dv, f16)))
-            w.conv_b[j] = nv.ptr(hold(_dev(sd[f"{p}input_embed.conv_pos_embed.conv1d.{idx}.bias"], dv, f32)))
+                return _dev(cw.permute(2, 0, 1).reshape(taps * D, gc), dv, f16)
+            dense = torch.zeros(taps, D, D)  # block-diagonal dense: out channel o reads its own group's inputs only
+            for g in range(groups):
+                dense[:, g * gc:(g + 1) * gc, g * gc:(g + 1) * gc] = cw[g * gc:(g + 1) * gc].permute(2, 0, 1)
+            return _dev(dense.reshape(taps * D, D), dv, f16)
 
-        w_proj = torch.zeros(128, D)
-        w_proj[:M] = sd[p + "proj_out.weight"].float()
-        w.w_proj = nv.ptr(hold(_dev(w_proj, dv, f16)))
-        w.b_proj = nv.ptr(hold(_dev(sd[p + "proj_out.bias"], dv, f32)))
+        for j, idx in enumerate((0, 2)):
+            w.conv_w[j] = take(f"conv_w{j}", lambda idx=idx: conv_weight(idx))
+            w.conv_b[j] = take(f"conv_b{j}",
+                               lambda idx=idx: _dev(sd[f"{p}input_embed.conv_pos_embed.conv1d.{idx}.bias"], dv, f32))
+
+        def proj_out():
+            w_proj = torch.zeros(128, D)
+            w_proj[:M] = sd[p + "proj_out.weight"].float()
+            return _dev(w_proj, dv, f16)
+
+        w.w_proj = take("w_proj", proj_out)
+        w.b_proj = take("b_proj", lambda: _dev(sd[p + "proj_out.bias"], dv, f32))
 
         layers = (nv.DitLayer * depth)()
         for i in range(depth):
             q = f"{p}transformer_blocks.{i}."
-            wqkv = torch.cat([sd[q + f"attn.to_{n}.weight"].float() for n in "qkv"], 0)
-            bqkv = torch.cat([sd[q + f"attn.to_{n}.bias"].float() for n in "qkv"], 0)
             L = layers[i]
-            L.w_qkv, L.b_qkv = nv.ptr(hold(_dev(wqkv, dv, f16))), nv.ptr(hold(_dev(bqkv, dv, f32)))
-            L.w_out = nv.ptr(hold(_dev(sd[q + "attn.to_out.0.weight"], dv, f16)))
-            L.b_out = nv.ptr(hold(_dev(sd[q + "attn.to_out.0.bias"], dv, f32)))
-            L.w_ff1 = nv.ptr(hold(_dev(sd[q + "ff.ff.0.0.weight"], dv, f16)))
-            L.b_ff1 = nv.ptr(hold(_dev(sd[q + "ff.ff.0.0.bias"], dv, f32)))
-            L.w_ff2 = nv.ptr(hold(_dev(sd[q + "ff.ff.2.weight"], dv, f16)))
-            L.b_ff2 = nv.ptr(hold(_dev(sd[q + "ff.ff.2.bias"], dv, f32)))
+            L.w_qkv = take(f"l{i}.w_qkv", lambda q=q: _dev(
+                torch.cat([sd[q + f"attn.to_{n}.weight"].float() for n in "qkv"], 0), dv, f16))
+            L.b_qkv = take(f"l{i}.b_qkv", lambda q=q: _dev(
+                torch.cat([sd[q + f"attn.to_{n}.bias"].float() for n in "qkv"], 0), dv, f32))
+            L.w_out = take(f"l{i}.w_out", lambda q=q: _dev(sd[q + "attn.to_out.0.weight"], dv, f16))
+            L.b_out = take(f"l{i}.b_out", lambda q=q: _dev(sd[q + "attn.to_out.0.bias"], dv, f32))
+            L.w_ff1 = take(f"l{i}.w_ff1", lambda q=q: _dev(sd[q + "ff.ff.0.0.weight"], dv, f16))
+            L.b_ff1 = take(f"l{i}.b_ff1", lambda q=q: _dev(sd[q + "ff.ff.0.0.bias"], dv, f32))
+            L.w_ff2 = take(f"l{i}.w_ff2", lambda q=q: _dev(sd[q + "ff.ff.2.weight"], dv, f16))
+            L.b_ff2 = take(f"l{i}.b_ff2", lambda q=q: _dev(sd[q + "ff.ff.2.bias"], dv, f32))
         self._layers = layers
         w.layers = layers
         self._weights = w
@@ -124,13 +145,46 @@ class DiTEngine:
         self._handle = handle
 
         # RotaryEmbedding.forward_from_seq_len (x-transformers): angle[n, j] = n * inv_freq[j]; (cos, sin) pairs.
-        inv_freq = sd.get(p + "rotary_embed.inv_freq")
-        if inv_freq is None:
-            inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
-        ang = torch.outer(torch.arange(4096, dtype=f32), inv_freq.detach().float().cpu())
-        self._rope = torch.stack((ang.cos(), ang.sin()), dim=-1).to(dv).contiguous()  # [4096, 32, 2]
+        def rope():
+            inv_freq = sd.get(p + "rotary_embed.inv_freq")
+            if inv_freq is None:
+                inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+            ang = torch.outer(torch.arange(4096, dtype=f32), inv_freq.detach().float().cpu())
+            return torch.stack((ang.cos(), ang.sin()), dim=-1).to(dv).contiguous()  # [4096, 32, 2]
+
+        take("rope", rope)
+        self._rope = self._packed["rope"]
         self._ws = None
         self._traj = None  # persistent trajectory staging buffer (stable address for the step graph)
+
+    # ------------------------------------------------------------------------------------------------ packed blob
+    def export_blob(self, path) -> None:
+        """Write the packed weights (what the kernels read: 0.37 GB of fp16 K-major GEMM operands + 0.55 GB of fp32
+        AdaLN / time matrices for the full model) to ONE safetensors file, so that the next start uploads them as they
+        are instead of re-deriving them from the 368-tensor fp32 checkpoint."""
+        import json
+
+        from safetensors.torch import save_file
+
+        meta = dict(version=str(self.BLOB_VERSION), arch=json.dumps(dict(
+            dim=self.dim, depth=self.depth, heads=self.heads, ff_mult=self.ff_mult, text_dim=self.text_dim,
+            mel_dim=self.mel_dim, pe_attn_head=self.pe_attn_head)))
+        save_file({k: v.detach().cpu().contiguous() for k, v in self._packed.items()}, str(path), metadata=meta)
+
+    @classmethod
+    def from_blob(cls, path, device="cuda") -> "DiTEngine":
+        """Engine from a file written by `export_blob` (tensors are read straight onto the device)."""
+        import json
+
+        from safetensors import safe_open
+
+        with safe_open(str(path), framework="pt", device=str(device)) as f:
+            meta = f.metadata() or {}
+            if meta.get("version") != str(cls.BLOB_VERSION):
+                raise RuntimeError(f"lemas_b200 error: {path} is not a version-{cls.BLOB_VERSION} packed weight blob")
+            packed = {k: f.get_tensor(k) for k in f.keys()}
+        arch = json.loads(meta["arch"])
+        return cls(None, device=device, prefix="", packed=packed, **arch)
 
     def __del__(self):
         h = getattr(self, "_handle", None)

@@ -190,10 +190,28 @@ class DiT(nn.Module):
                                    "Blackwell device (no kernel image is available for execution on the device)")
             from ...engine import DiTEngine
 
+            import os
+            from pathlib import Path
+
             sd = {k: v for k, v in self.state_dict().items()}
-            self._engine = DiTEngine(sd, dim=self.dim, depth=self.depth, heads=self.heads, ff_mult=self.ff_mult,
-                                     text_dim=self.text_dim, mel_dim=self.mel_dim, pe_attn_head=self.pe_attn_head,
-                                     qk_norm=self.qk_norm, device=dev, prefix="")
+            # LEMAS_PACKED_CACHE=<dir>: the packed (fp16, re-laid-out) weights are written once per checkpoint content
+            # and uploaded as they are on later starts instead of being re-derived from the fp32 tensors
+            cache = os.environ.get("LEMAS_PACKED_CACHE")
+            blob = None
+            if cache and self.qk_norm is None:
+                only = {k: v for k, v in sd.items() if not k.startswith("text_embed.") and "prosody" not in k}
+                blob = Path(cache) / f"dit_{nv.state_fingerprint(only)}.safetensors"
+            if blob is not None and blob.is_file():
+                self._engine = DiTEngine.from_blob(blob, device=dev)
+            else:
+                self._engine = DiTEngine(sd, dim=self.dim, depth=self.depth, heads=self.heads, ff_mult=self.ff_mult,
+                                         text_dim=self.text_dim, mel_dim=self.mel_dim, pe_attn_head=self.pe_attn_head,
+                                         qk_norm=self.qk_norm, device=dev, prefix="")
+                if blob is not None:
+                    blob.parent.mkdir(parents=True, exist_ok=True)
+                    tmp = blob.with_suffix(f".tmp{os.getpid()}")
+                    self._engine.export_blob(tmp)
+                    os.replace(tmp, blob)
             self._engine_key = key
         return self._engine
 

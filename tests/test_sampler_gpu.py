@@ -190,3 +190,34 @@ def test_graph_cache_is_keyed_by_step_count():
     g16, _ = model.sample(**kw, steps=16, return_trajectory=False)
     e16, _ = model.sample(**kw, steps=16, return_trajectory=True)
     assert torch.equal(g5, e5) and torch.equal(g16, e16)
+
+
+def test_packed_weight_blob_roundtrip(tmp_path, monkeypatch):
+    """the packed weights written by the first start (LEMAS_PACKED_CACHE) are what a later start
+    uploads — same bits out of the sampler, no re-packing of the fp32 checkpoint tensors."""
+    import time
+
+    from lemas_tts.engine import DiTEngine
+
+    case = gc.CASES["sample_tiny_b1"]
+    inp = gc.inputs(case)
+    arch = getattr(syn, case["arch"])
+    kw = dict(cond=inp["cond"].cuda(), text=inp["text"].cuda(), duration=inp["duration"], steps=3, cfg_strength=2.0,
+              sway_sampling_coef=3.0, use_acc_grl=False, noise=inp["noise"], return_trajectory=False)
+    ref, _ = _build(arch, case["wseed"]).sample(**kw)          # no cache
+    monkeypatch.setenv("LEMAS_PACKED_CACHE", str(tmp_path))
+    first = _build(arch, case["wseed"])
+    out1, _ = first.sample(**kw)                                 # packs and writes the blob
+    blobs = list(tmp_path.glob("dit_*.safetensors"))
+    assert len(blobs) == 1
+    t0 = time.perf_counter()
+    second = _build(arch, case["wseed"])
+    out2, _ = second.sample(**kw)                                # loads the blob
+    assert isinstance(second.transformer.engine(), DiTEngine) and len(list(tmp_path.glob("dit_*"))) == 1
+    assert torch.equal(ref, out1) and torch.equal(ref, out2)
+    other = _build(arch, case["wseed"] + 1)                      # different weights -> different blob
+    other.sample(**kw)
+    assert len(list(tmp_path.glob("dit_*.safetensors"))) == 2
+    eng = DiTEngine.from_blob(blobs[0])
+    assert (eng.dim, eng.depth, eng.heads) == (arch.dim, arch.depth, arch.heads)
+    print(f"second start with the blob: {time.perf_counter() - t0:.2f} s")
