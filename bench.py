@@ -536,15 +536,18 @@ def run_b200(args):
             kinds[k] = {"ms": round(ms, 3), "launches": n, "share": round(ms / prof_ms, 4)}
     gemm_flops = {"gemm_qkv": 2.0 * 3 * D * D, "gemm_out": 2.0 * D * D, "gemm_ff1": 2.0 * D * D * arch.ff_mult,
                   "gemm_ff2": 2.0 * D * D * arch.ff_mult}
+    # rows the GEMMs usefully process per launch: every row of a uniform batch; the VALID rows of a ragged one (padded
+    # rows are either skipped or computed for nothing — neither counts as work)
+    rows_alg = sum(d for _, d in wl.gen_slices) if wl.name == "C3" else N * batch
     for k, per_tok in gemm_flops.items():
         ms, n = prof[k]
         if n:
-            kinds[k]["tflops"] = round(per_tok * N * batch * variants / (ms / n * 1e-3) / 1e12, 1)
+            kinds[k]["tflops"] = round(per_tok * rows_alg * variants / (ms / n * 1e-3) / 1e12, 1)
     if att_n:
         kinds["attention"]["tflops"] = round(att_tflops, 1)
     ms, n = prof["ln_mod"]
     if n:  # algorithmic bytes: read fp32 x, write fp16 (6 B / element)
-        kinds["ln_mod"]["gbs"] = round(6.0 * D * N * batch * variants / (ms / n * 1e-3) / 1e9, 1)
+        kinds["ln_mod"]["gbs"] = round(6.0 * D * rows_alg * variants / (ms / n * 1e-3) / 1e9, 1)
 
     value = world * frames * args.steps / (ms_total * 1e-3)
     e2e = world * frames * args.steps / (ms_e2e * 1e-3)
