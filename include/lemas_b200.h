@@ -88,6 +88,15 @@ typedef struct lemas_gemm_desc {
   const int32_t* row_limit;  /* optional, device int32 [sequences]: 256-row tiles that start at or beyond row_limit[b]
                                 of their sequence are not computed at all (ragged batches, see lemas_sample_args.flags);
                                 honoured by the CTA-pair kernel (block_n 256), NULL = every row                       */
+  /* LayerNorm folded into the GEMMs around it (CTA-pair kernel only; all NULL = off).
+   * Producer (LEMAS_EPI_GATE_RESID_F32): besides out32 = x_new, write ln_out16 = fp16(x_new * fp16(1 + ln_scale[col]))
+   * and the per-row partial (sum, sum of squares) of x_new over each 128-column slice: ln_stats fp32
+   * [rows][n / 128][2].  Consumer (QKV_ROPE / GELU epilogues, A = that ln_out16): acc -> rstd (acc - mean u[col]) +
+   * v[col] with mean / rstd (eps 1e-6) from the ln_parts partials of ln_stats_in, and u = ln_uv[2 step][col],
+   * v = ln_uv[2 step + 1][col] (fp32 [2 steps, n]: u = W (1 + scale), v = W shift for every ODE step, hoisted), step =
+   * *ln_step - 1.  Algebraically LayerNorm(x) (1 + scale) + shift fed to the same GEMM (modules.py:314, 637). */
+  const float* ln_scale; void* ln_out16; int32_t ln_ld16; float* ln_stats;
+  const float* ln_stats_in; int32_t ln_parts; const float* ln_uv; const int32_t* ln_step; int32_t ln_k;
 } lemas_gemm_desc;
 
 int lemas_gemm_f16(const lemas_gemm_desc* d, void* stream);
@@ -213,6 +222,10 @@ typedef struct lemas_sample_args {
                                  of the returned state then differ from the reference's (callers slice them off).     */
 } lemas_sample_args;
 #define LEMAS_SAMPLE_SKIP_PADDED_ROWS 1
+/* Fold every LayerNorm except layer 0's attn_norm and the final norm into the GEMMs around it (lemas_gemm_desc.ln_*):
+ * 64 instead of 1 440 LayerNorm launches per 32-step utterance, same parity — but 1.2 % SLOWER end to end on C2 (the
+ * extra epilogue work costs more than the 5 us kernel it replaces), so it is off unless asked for. */
+#define LEMAS_SAMPLE_FOLD_LAYERNORM 2
 
 /* CFM.sample's ODE loop (cfm.py:382-456): `steps` Euler steps of the CFG-combined DiT flow. */
 int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream);

@@ -261,6 +261,34 @@ int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const 
   return LEMAS_OK;
 }
 
+// Folded LayerNorm, pre-loop: A operands of the u / v GEMMs.  For layer l and norm w (0 = attn_norm, 1 = ff_norm) the
+// matrix [2 steps, dim] holds row 2 s = fp16(1 + scale_{s,l,w}) and row 2 s + 1 = fp16(shift_{s,l,w}), read from the
+// all-steps modulation table (chunk order shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp; modules.py:312).
+__global__ void ln_fold_pack_kernel(const float* __restrict__ mod, long mod_w, int steps, int depth, int dim,
+                                    __half* __restrict__ out) {
+  const long total = (long)depth * 2 * 2 * steps * dim;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dim);
+    long t = i / dim;
+    const int row = (int)(t % (2 * steps));
+    t /= 2 * steps;
+    const int w = (int)(t & 1), l = (int)(t >> 1);
+    const int s = row >> 1, is_shift = row & 1;
+    const float* m = mod + (long)s * mod_w + (long)l * 6 * dim + (w ? 3 * dim : 0);   // shift, scale of this norm
+    const float v = is_shift ? m[c] : 1.0f + m[dim + c];
+    out[i] = __float2half_rn(v);
+  }
+}
+
+int ln_fold_pack_launch(const float* mod, long mod_w, int steps, int depth, int dim, void* out16, cudaStream_t st) {
+  const long total = (long)depth * 4 * steps * dim;
+  long grid = (total + 255) / 256;
+  if (grid > (long)sm_count() * 16) grid = (long)sm_count() * 16;
+  ln_fold_pack_kernel<<<(int)grid, 256, 0, st>>>(mod, mod_w, steps, depth, dim, (__half*)out16);
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
 int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
                          long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st) {
   const long total = (long)rows * mel;

@@ -17,6 +17,7 @@ int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const 
                       cudaStream_t st);
 int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
                          long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st);
+int ln_fold_pack_launch(const float* mod, long mod_w, int steps, int depth, int dim, void* out16, cudaStream_t st);
 
 struct Carver {
   uint8_t* base;
@@ -35,6 +36,8 @@ struct DitBuffers {
   __half *x16, *ct16, *h0_16, *c1_16, *a16, *o16, *qk16, *vt16, *ff16;
   float *inv_embed, *h0, *x, *pred, *t_dev, *sinus, *t1, *temb, *mod, *mod_cur, *state, *y_state;
   int *kv_len2, *step_ctr, *row_limit;
+  __half* ln_a16;     // folded LayerNorm: [depth][2 norms][2 steps][dim] fp16 (1 + scale | shift rows)
+  float *ln_uv_qkv, *ln_uv_ff1, *ln_stats;   // [depth][2 steps][3 inner] / [depth][2 steps][F] / [M2][8][2]
   int npad;
   int64_t bytes;
 };
@@ -69,6 +72,10 @@ static DitBuffers carve(const lemas_dit_config& c, int batch, int seq, int steps
   b.state = cv.take<float>(4);
   b.step_ctr = cv.take<int>(1);
   b.y_state = cv.take<float>((int64_t)batch * seq * c.mel_dim);
+  b.ln_a16 = cv.take<__half>((int64_t)c.depth * 4 * steps * D);
+  b.ln_uv_qkv = cv.take<float>((int64_t)c.depth * 2 * steps * 3 * inner);
+  b.ln_uv_ff1 = cv.take<float>((int64_t)c.depth * 2 * steps * F);
+  b.ln_stats = cv.take<float>(M2 * 16);
   b.bytes = align_up(cv.off, 1024);
   return b;
 }
@@ -210,8 +217,11 @@ static lemas_gemm_desc base_desc(const void* a, int batches, int rows, int lda, 
 }
 
 // One DiT forward on `variants*batch` co-batched sequences; mod = this step's modulation row.
+// fold_steps > 0: LayerNorm of every block except layer 0's attn_norm and the final norm is folded into the GEMMs
+// around it (lemas_gemm_desc.ln_*); the u / v tables for `fold_steps` ODE steps were built by prepare().
 static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, int seq, int variants, const float* mod,
-                       const int* kv_len2, const float* rope, float* pred, const int* row_limit, cudaStream_t st) {
+                       const int* kv_len2, const float* rope, float* pred, const int* row_limit, int fold_steps,
+                       cudaStream_t st) {
   const lemas_dit_config& c = e->cfg;
   const lemas_dit_weights& w = e->w;
   const int D = c.dim, inner = c.heads * 64, F = c.dim * c.ff_mult;
@@ -241,9 +251,18 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
   for (int l = 0; l < c.depth; ++l) {
     const lemas_dit_layer& L = w.layers[l];
     const float* m = mod + (int64_t)l * 6 * D;  // shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp
-    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + D, m, 0, b.a16, M, D, seq, row_limit, st)); }
+    const bool fold = fold_steps > 0;
+    const int parts = 2 * (D / 256);   // 128-column partials per row written by the gated-residual epilogues
+    if (!fold || l == 0) {
+      PROF(LEMAS_PROF_LN_MOD);
+      LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + D, m, 0, b.a16, M, D, seq, row_limit, st));
+    }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_qkv, 3 * inner, D, 3 * inner, seq, LEMAS_EPI_QKV_ROPE, 256);
+      if (fold && l > 0) {  // A = x (1 + scale_msa) written by the previous layer's FF2 epilogue
+        d.ln_stats_in = b.ln_stats; d.ln_parts = parts; d.ln_k = D; d.ln_step = b.step_ctr;
+        d.ln_uv = b.ln_uv_qkv + (int64_t)l * 2 * fold_steps * 3 * inner;
+      }
       d.bias = L.b_qkv; d.out16 = b.qk16; d.ld16 = 2 * inner; d.rope = rope;
       d.rope_cols = c.rope_heads * 64; d.inner = inner; d.vt = b.vt16; d.vt_ld = b.npad;
       d.row_limit = row_limit;
@@ -259,14 +278,22 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
       d.bias = L.b_out; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 2 * D; d.gate_bstride = 0;
       d.row_valid = kv_len2;
       d.row_limit = row_limit;
+      if (fold) { d.ln_scale = m + 4 * D; d.ln_out16 = b.a16; d.ln_ld16 = D; d.ln_stats = b.ln_stats; }  // ff_norm
       PROF(LEMAS_PROF_GEMM_OUT);
       LEMAS_TRY(gemm_launch(d, st));
     }
-    { PROF(LEMAS_PROF_LN_MOD); LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, row_limit, st)); }
+    if (!fold) {
+      PROF(LEMAS_PROF_LN_MOD);
+      LEMAS_TRY(lemas_ln_modulate_rows(b.x, m + 4 * D, m + 3 * D, 0, b.a16, M, D, seq, row_limit, st));
+    }
     {
       lemas_gemm_desc d = base_desc(b.a16, 1, M, D, L.w_ff1, F, D, F, seq, LEMAS_EPI_GELU_TANH_F16, 256);
       d.bias = L.b_ff1; d.out16 = b.ff16; d.ld16 = F;
       d.row_limit = row_limit;
+      if (fold) {
+        d.ln_stats_in = b.ln_stats; d.ln_parts = parts; d.ln_k = D; d.ln_step = b.step_ctr;
+        d.ln_uv = b.ln_uv_ff1 + (int64_t)l * 2 * fold_steps * F;
+      }
       PROF(LEMAS_PROF_GEMM_FF1);
       LEMAS_TRY(gemm_launch(d, st));
     }
@@ -274,6 +301,9 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
       lemas_gemm_desc d = base_desc(b.ff16, 1, M, F, L.w_ff2, D, F, D, seq, LEMAS_EPI_GATE_RESID_F32, bn_d);
       d.bias = L.b_ff2; d.resid = b.x; d.ldr = D; d.out32 = b.x; d.ld32 = D; d.gate = m + 5 * D; d.gate_bstride = 0;
       d.row_limit = row_limit;
+      if (fold && l + 1 < c.depth) {  // attn_norm of the next layer: its scale_msa sits 6 D further in the row
+        d.ln_scale = m + 6 * D + D; d.ln_out16 = b.a16; d.ln_ld16 = D; d.ln_stats = b.ln_stats;
+      }
       PROF(LEMAS_PROF_GEMM_FF2);
       LEMAS_TRY(gemm_launch(d, st));
     }
@@ -291,8 +321,16 @@ static int dit_forward(const lemas_engine* e, const DitBuffers& b, int batch, in
 
 // Everything that does not depend on the ODE state: time embeddings + all AdaLN modulations for every step
 // (modules.py:311,332,725 hoisted), the (cond|text) half of the input projection, fp16 copy of y0.
+// LEMAS_SAMPLE_FOLD_LAYERNORM: fold the LayerNorms into the GEMMs around them (off by default: measured 1.2 % slower
+// at C2 than the stand-alone kernel).  Needs the CTA-pair GEMM on every projection it touches.
+static bool fold_ok(const lemas_engine* e, const lemas_sample_args* a) {
+  const lemas_dit_config& c = e->cfg;
+  return (a->flags & LEMAS_SAMPLE_FOLD_LAYERNORM) != 0 && c.dim % 256 == 0 && (c.dim * c.ff_mult) % 256 == 0 &&
+         (3 * c.heads * 64) % 256 == 0;
+}
+
 static int prepare(const lemas_engine* e, const DitBuffers& b, const lemas_sample_args* a, int variants, int n_times,
-                   const float* times_host, cudaStream_t st) {
+                   const float* times_host, int fold_steps, cudaStream_t st) {
   const lemas_dit_config& c = e->cfg;
   const lemas_dit_weights& w = e->w;
   const int D = c.dim;
@@ -304,6 +342,21 @@ static int prepare(const lemas_engine* e, const DitBuffers& b, const lemas_sampl
   LEMAS_TRY(lemas_skinny_linear_f32(b.sinus, w.time_w0, w.time_b0, b.t1, n_times, 256, D, 0, 1, st));
   LEMAS_TRY(lemas_skinny_linear_f32(b.t1, w.time_w2, w.time_b2, b.temb, n_times, D, D, 0, 0, st));
   LEMAS_TRY(lemas_skinny_linear_f32(b.temb, w.adaln_w, w.adaln_b, b.mod, n_times, D, (int)mod_w, 1, 0, st));
+  if (fold_steps > 0) {
+    // u[n] = sum_k W[n,k] (1 + scale_k), v[n] = sum_k W[n,k] shift_k for every step, layer and folded norm: one small
+    // GEMM per (layer, norm) over the fp16 weights the main GEMMs use (so the mean term cancels exactly)
+    const int inner = c.heads * 64, F = c.dim * c.ff_mult, R = 2 * fold_steps;
+    LEMAS_TRY(ln_fold_pack_launch(b.mod, mod_w, fold_steps, c.depth, D, b.ln_a16, st));
+    for (int l = 0; l < c.depth; ++l)
+      for (int wsel = 0; wsel < 2; ++wsel) {
+        const int N = wsel == 0 ? 3 * inner : F;
+        lemas_gemm_desc d = base_desc(b.ln_a16 + ((int64_t)(l * 2 + wsel) * R) * D, 1, R, D,
+                                      wsel == 0 ? w.layers[l].w_qkv : w.layers[l].w_ff1, N, D, N, R, LEMAS_EPI_BIAS_F32, 256);
+        d.out32 = (wsel == 0 ? b.ln_uv_qkv + (int64_t)l * R * N : b.ln_uv_ff1 + (int64_t)l * R * N);
+        d.ld32 = N;
+        LEMAS_TRY(gemm_launch(d, st));
+      }
+  }
   LEMAS_TRY(lemas_cast_pad_f16(a->y, b.x16, rows, c.mel_dim, 128, variants, st));
   LEMAS_TRY(lemas_pack_cond_text(a->step_cond, a->text_cond, a->text_uncond, b.ct16, rows, c.mel_dim, c.text_dim,
                                  w.ct_ld, variants, st));
@@ -350,7 +403,8 @@ static int ode_step(lemas_engine* e, const DitBuffers& b, const lemas_sample_arg
                                 variants == 2 ? a->cfg_strength : 0.f, row_limit, kv2, variants * a->batch, a->seq,
                                 a->steps, st));
   }
-  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, row_limit, st));
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, row_limit,
+                        fold_ok(e, a) ? a->steps : 0, st));
   PROF(LEMAS_PROF_CFG_EULER);
   LEMAS_TRY(cfg_euler_dev_launch(b.pred, 128, y, b.x16, 128, variants, a->trajectory, (long)rows * c.mel_dim, rows,
                                  c.mel_dim, b.state, variants == 2 ? 1 : 0, st));
@@ -366,7 +420,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   LEMAS_REQUIRE(variants == 1 || a->text_uncond, "lemas_sampler_run: text_uncond required when cfg_strength > 0");
   const lemas_dit_config& c = e->cfg;
   const int rows = a->batch * a->seq;
-  LEMAS_TRY(prepare(e, b, a, variants, a->steps, a->t_grid_host, st));
+  LEMAS_TRY(prepare(e, b, a, variants, a->steps, a->t_grid_host, fold_ok(e, a) ? a->steps : 0, st));
   // prepare() uploaded t[0..steps-1]; the step kernels also need t[steps] for the last dt
   LEMAS_CUDA_OK(cudaMemcpyAsync(b.t_dev + a->steps, a->t_grid_host + a->steps, sizeof(float), cudaMemcpyHostToDevice, st));
   LEMAS_CUDA_OK(cudaMemsetAsync(b.step_ctr, 0, sizeof(int), st));
@@ -483,8 +537,8 @@ int lemas_dit_forward(lemas_engine* e, const lemas_sample_args* a, float t, floa
   DitBuffers b;
   LEMAS_TRY(check_args(e, a, 1, &b));
   LEMAS_REQUIRE(pred && a->text_uncond, "lemas_dit_forward: pred and text_uncond are required");
-  LEMAS_TRY(prepare(e, b, a, 2, 1, &t, st));
-  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, 2, b.mod, a->kv_len ? b.kv_len2 : nullptr, a->rope, pred, nullptr, st));
+  LEMAS_TRY(prepare(e, b, a, 2, 1, &t, 0, st));
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, 2, b.mod, a->kv_len ? b.kv_len2 : nullptr, a->rope, pred, nullptr, 0, st));
   if (hidden_out)
     LEMAS_CUDA_OK(cudaMemcpyAsync(hidden_out, b.x, sizeof(float) * 2LL * a->batch * a->seq * e->cfg.dim,
                                   cudaMemcpyDeviceToDevice, st));

@@ -350,6 +350,9 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   p.resid = d.resid; p.ldr = d.ldr;
   p.gate = d.gate; p.gate_bstride = d.gate_bstride;
   p.row_valid = d.row_valid; p.seq_len = d.seq_len; p.row_limit = d.row_limit;
+  p.ln_scale = d.ln_scale; p.ln_out16 = static_cast<__half*>(d.ln_out16); p.ln_ld16 = d.ln_ld16; p.ln_stats = d.ln_stats;
+  p.ln_stats_in = d.ln_stats_in; p.ln_parts = d.ln_parts; p.ln_uv = d.ln_uv; p.ln_step = d.ln_step;
+  p.ln_inv_k = d.ln_k > 0 ? 1.0f / (float)d.ln_k : 0.f;
   p.rope = reinterpret_cast<const float2*>(d.rope); p.rope_cols = d.rope_cols; p.inner = d.inner;
   p.vt = static_cast<__half*>(d.vt); p.vt_ld = d.vt_ld;
 
@@ -371,6 +374,8 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
                   "lemas_gemm_f16: QKV epilogue needs rope table, vt buffer and n == 3*inner");
 
   if (pair_enabled() && gemm2_eligible(d)) return gemm2_launch(d, p, stream);
+  LEMAS_REQUIRE(d.ln_out16 == nullptr && d.ln_stats_in == nullptr,
+                "lemas_gemm_f16: the folded LayerNorm needs the CTA-pair kernel (block_n 256, n % 256 == 0)");
 
   CUtensorMap tmA, tmW;
   {

@@ -40,7 +40,8 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_PITCH = 36;                           // floats per staged row (32 + 4: conflict-free float4 access)
 constexpr int G2_STG_BYTES = G2_EPI_WARPS * 32 * G2_PITCH * 4;
 constexpr int G2_OFF_STG = G2_STAGES * G2_STAGE_BYTES;
-constexpr int G2_OFF_BAR = G2_OFF_STG + G2_STG_BYTES;
+constexpr int G2_OFF_LNS = G2_OFF_STG + G2_STG_BYTES;                 // folded LayerNorm: float2 [epi warps][32 rows]
+constexpr int G2_OFF_BAR = G2_OFF_LNS + G2_EPI_WARPS * 32 * 8;
 constexpr int G2_SMEM = G2_OFF_BAR + 256 + 1024;
 
 DEVI uint2 pack4_half(float4 v) { return make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w)); }
@@ -84,9 +85,19 @@ DEVI void epi2_prefetch(const GemmParams& p, const RowCtx& rc, int col0, int lan
 
 // One 32-row x 32-column block of the accumulator.  r[i] = acc[row lane of the warp][col0 + i].
 // bias4 / gate4: this thread's 4 columns (col0 + 4*(lane&7) ..) of the per-column vectors.
-template <int EPI>
+// Folded LayerNorm, per-thread state of one tile.  Consumer side: mean / rstd of the 8 rows this thread touches in the
+// transposed layout (row it*4 + lane/8) and of row `lane` (the lane-per-row V path); producer side: running partial
+// (sum, sum of squares) of those 8 rows over the warp's 128 columns.
+struct LnState {
+  float mu[8], rs[8];
+  float mu_l, rs_l;
+  float2* acc;   // producer: this warp's shared-memory accumulators, one (sum, sum of squares) per row
+};
+
+template <int EPI, bool FOLD>
 DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], const RowCtx& rc, int col0, int lane,
-                     float4 bias4, float4 gate4, const float4 (&pre)[8]) {
+                     float4 bias4, float4 gate4, const float4 (&pre)[8], LnState& ln, float4 lnu4, float4 lnv4,
+                     const float* ln_u, const float* ln_v) {
   if constexpr (EPI == LEMAS_EPI_QKV_ROPE) {
     if (col0 >= 2 * p.inner) {
       // V: transposed copy vt[b, head, d, pos].  The block is transposed through shared memory as fp16 so that each
@@ -98,12 +109,21 @@ DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], c
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         bv[j] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr bool fold = FOLD;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        sth[(4 * j + 0) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 0]) + bv[j].x);
-        sth[(4 * j + 1) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 1]) + bv[j].y);
-        sth[(4 * j + 2) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 2]) + bv[j].z);
-        sth[(4 * j + 3) * 40 + lane] = __float2half_rn(__uint_as_float(r[4 * j + 3]) + bv[j].w);
+        float4 a = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+        if (fold) {  // acc -> rstd (acc - mean u) + v for this lane's row
+          const float4 u = __ldg(reinterpret_cast<const float4*>(ln_u + col0) + j);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(ln_v + col0) + j);
+          a.x = ln.rs_l * (a.x - ln.mu_l * u.x) + w.x; a.y = ln.rs_l * (a.y - ln.mu_l * u.y) + w.y;
+          a.z = ln.rs_l * (a.z - ln.mu_l * u.z) + w.z; a.w = ln.rs_l * (a.w - ln.mu_l * u.w) + w.w;
+        }
+        sth[(4 * j + 0) * 40 + lane] = __float2half_rn(a.x + bv[j].x);
+        sth[(4 * j + 1) * 40 + lane] = __float2half_rn(a.y + bv[j].y);
+        sth[(4 * j + 2) * 40 + lane] = __float2half_rn(a.z + bv[j].z);
+        sth[(4 * j + 3) * 40 + lane] = __float2half_rn(a.w + bv[j].w);
       }
       __syncwarp();
       __half* dst0 = p.vt + ((long)(rc.b * heads + (vcol >> 6)) * 64 + (vcol & 63)) * p.vt_ld + rc.pos0;
@@ -142,6 +162,13 @@ DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], c
     if (rr >= rc.nrows) continue;
     const long grow = rc.grow0 + rr;
     float4 v = *reinterpret_cast<const float4*>(stg + rr * G2_PITCH + c4 * 4);
+    if constexpr (FOLD && (EPI == LEMAS_EPI_QKV_ROPE || EPI == LEMAS_EPI_GELU_TANH_F16)) {
+      {  // folded LayerNorm: acc -> rstd (acc - mean u[col]) + v[col]
+        const float m = ln.mu[it], rsd = ln.rs[it];
+        v.x = rsd * (v.x - m * lnu4.x) + lnv4.x; v.y = rsd * (v.y - m * lnu4.y) + lnv4.y;
+        v.z = rsd * (v.z - m * lnu4.z) + lnv4.z; v.w = rsd * (v.w - m * lnu4.w) + lnv4.w;
+      }
+    }
     v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
     if constexpr (EPI == LEMAS_EPI_GATE_RESID_F32) {
       float4 g = gate4;
@@ -151,6 +178,27 @@ DEVI void epi2_block(const GemmParams& p, float* stg, const uint32_t (&r)[32], c
       float4 o = pre[it];
       if (!dead) { o.x += g.x * v.x; o.y += g.y * v.y; o.z += g.z * v.z; o.w += g.w * v.w; }
       *reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + col) = o;
+      if constexpr (FOLD) {
+        // folded LayerNorm, producer: the next GEMM's A operand is x_new (1 + scale) — UN-normalised, the row
+        // statistics are applied in that GEMM's epilogue — plus this row's partial sums over the thread's 4 columns,
+        // reduced over the 8 lanes that share the row (lnu4 carries the fp16-rounded 1 + scale here)
+        *reinterpret_cast<uint2*>(p.ln_out16 + grow * p.ln_ld16 + col) =
+            pack4_half(make_float4(o.x * lnu4.x, o.y * lnu4.y, o.z * lnu4.z, o.w * lnu4.w));
+        float sm = (o.x + o.y) + (o.z + o.w);
+        float sq = (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+        const unsigned grp = 0xFFu << (rsub * 8);
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          sm += __shfl_xor_sync(grp, sm, off);
+          sq += __shfl_xor_sync(grp, sq, off);
+        }
+        if (c4 == 0) {  // one lane per row owns the accumulator; the 4 column blocks of a tile come one after the other
+          float2 a = ln.acc[rr];
+          a.x += sm;
+          a.y += sq;
+          ln.acc[rr] = a;
+        }
+      }
     } else if constexpr (EPI == LEMAS_EPI_BIAS_F16) {
       *reinterpret_cast<uint2*>(p.out16 + grow * p.ld16 + col) = pack4_half(v);
     } else if constexpr (EPI == LEMAS_EPI_GELU_TANH_F16) {
@@ -178,7 +226,7 @@ DEVI bool tile_skipped(const GemmParams& p, int batch_item, int first_row) {
   return p.row_limit != nullptr && first_row >= __ldg(p.row_limit + batch_item);
 }
 
-template <int EPI>
+template <int EPI, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ GemmParams p) {
@@ -312,23 +360,85 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (rc.nrows > 0) {
         float4 pre_nxt[8];
         epi2_prefetch<EPI>(p, rc, n0 + j0 * 32, lane, pre_nxt);  // does not depend on the accumulator either
+        // ---- folded LayerNorm (see lemas_gemm_desc): per-tile set-up, all from global memory written by earlier kernels
+        LnState ln;
+        const float* ln_u = nullptr;
+        const float* ln_v = nullptr;
+        constexpr bool ln_cons = FOLD && (EPI == LEMAS_EPI_QKV_ROPE || EPI == LEMAS_EPI_GELU_TANH_F16);
+        constexpr bool ln_prod = FOLD && EPI == LEMAS_EPI_GATE_RESID_F32;
+        if (ln_cons) {
+          const int step = __ldg(p.ln_step) - 1;
+          ln_u = p.ln_uv + (long)(2 * step) * p.n;
+          ln_v = ln_u + p.n;
+          const int c4 = lane & 7, rsub = lane >> 3;
+          const unsigned grp = 0xFFu << (rsub * 8);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {  // lane c4 fetches partial c4 of row it*4 + rsub; the 8 lanes add them up
+            const int rr = it * 4 + rsub;
+            float2 pt = make_float2(0.f, 0.f);
+            if (rr < rc.nrows && c4 < p.ln_parts)
+              pt = __ldg(reinterpret_cast<const float2*>(p.ln_stats_in) + (rc.grow0 + rr) * p.ln_parts + c4);
+#pragma unroll
+            for (int off = 1; off < 8; off <<= 1) {
+              pt.x += __shfl_xor_sync(grp, pt.x, off);
+              pt.y += __shfl_xor_sync(grp, pt.y, off);
+            }
+            const float mean = pt.x * p.ln_inv_k;
+            ln.mu[it] = mean;
+            ln.rs[it] = rsqrtf(fmaxf(pt.y * p.ln_inv_k - mean * mean, 0.f) + 1e-6f);
+          }
+          float sl = 0.f, ql = 0.f;  // row `lane` (the transposed V copy works lane-per-row)
+          if (lane < rc.nrows)
+            for (int k = 0; k < p.ln_parts; ++k) {
+              const float2 pt = __ldg(reinterpret_cast<const float2*>(p.ln_stats_in) + (rc.grow0 + lane) * p.ln_parts + k);
+              sl += pt.x;
+              ql += pt.y;
+            }
+          ln.mu_l = sl * p.ln_inv_k;
+          ln.rs_l = rsqrtf(fmaxf(ql * p.ln_inv_k - ln.mu_l * ln.mu_l, 0.f) + 1e-6f);
+        }
+        if (ln_prod) {
+          ln.acc = reinterpret_cast<float2*>(smem + G2_OFF_LNS) + (warp - 2) * 32;
+          ln.acc[lane] = make_float2(0.f, 0.f);
+          __syncwarp();
+        }
+        auto load_lnu = [&](int j) {  // consumer: u[col]; producer: fp16-rounded 1 + scale[col]
+          if (ln_cons) return __ldg(reinterpret_cast<const float4*>(ln_u + ccol + j * 32));
+          if (ln_prod) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.ln_scale + ccol + j * 32));
+            return make_float4(__half2float(__float2half_rn(1.f + sc.x)), __half2float(__float2half_rn(1.f + sc.y)),
+                               __half2float(__float2half_rn(1.f + sc.z)), __half2float(__float2half_rn(1.f + sc.w)));
+          }
+          return make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto load_lnv = [&](int j) {
+          return ln_cons ? __ldg(reinterpret_cast<const float4*>(ln_v + ccol + j * 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 lnu_nxt = make_float4(0.f, 0.f, 0.f, 0.f), lnv_nxt = lnu_nxt;
+        if constexpr (FOLD) { lnu_nxt = load_lnu(j0); lnv_nxt = load_lnv(j0); }
         mbar_wait(acc_full + acc, acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int j = j0; j < j0 + 4; ++j) {
-          const float4 bias4 = bias_nxt, gate4 = gate_nxt;
+          const float4 bias4 = bias_nxt, gate4 = gate_nxt, lnu4 = lnu_nxt, lnv4 = lnv_nxt;
           float4 pre[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) pre[i] = pre_nxt[i];
           if (j < j0 + 3) {
             bias_nxt = load_bias(j + 1);
             gate_nxt = load_gate(j + 1);
+            if constexpr (FOLD) { lnu_nxt = load_lnu(j + 1); lnv_nxt = load_lnv(j + 1); }
             epi2_prefetch<EPI>(p, rc, n0 + (j + 1) * 32, lane, pre_nxt);
           }
           uint32_t r[32];
           tmem_ld_32x32(t_addr + j * 32, r);
           tmem_ld_wait();
-          epi2_block<EPI>(p, stg, r, rc, n0 + j * 32, lane, bias4, gate4, pre);
+          epi2_block<EPI, FOLD>(p, stg, r, rc, n0 + j * 32, lane, bias4, gate4, pre, ln, lnu4, lnv4, ln_u, ln_v);
+        }
+        if (ln_prod) {  // this warp's 128-column partial of its 32 rows
+          __syncwarp();
+          const int parts = 2 * n_tiles, part = n_idx * 2 + half;
+          if (lane < rc.nrows) reinterpret_cast<float2*>(p.ln_stats)[(rc.grow0 + lane) * parts + part] = ln.acc[lane];
         }
       } else {
         mbar_wait(acc_full + acc, acc_phase);
@@ -347,10 +457,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
-template <int EPI>
+template <int EPI, bool FOLD = false>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st) {
   static unsigned long long configured = 0;
-  auto kern = gemm2_kernel<EPI>;
+  auto kern = gemm2_kernel<EPI, FOLD>;
   LEMAS_CUDA_OK(ensure_dynamic_smem(kern, G2_SMEM, configured));
   const int tiles = p.batches * ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
   int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
@@ -397,10 +507,16 @@ int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p_in, cudaStream_t 
   }
   switch (d.epilogue) {
     case LEMAS_EPI_BIAS_F16: return launch2<LEMAS_EPI_BIAS_F16>(tmA, tmW, p, d.max_ctas, st);
-    case LEMAS_EPI_QKV_ROPE: return launch2<LEMAS_EPI_QKV_ROPE>(tmA, tmW, p, d.max_ctas, st);
-    case LEMAS_EPI_GELU_TANH_F16: return launch2<LEMAS_EPI_GELU_TANH_F16>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_QKV_ROPE:
+      return p.ln_stats_in ? launch2<LEMAS_EPI_QKV_ROPE, true>(tmA, tmW, p, d.max_ctas, st)
+                           : launch2<LEMAS_EPI_QKV_ROPE>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_GELU_TANH_F16:
+      return p.ln_stats_in ? launch2<LEMAS_EPI_GELU_TANH_F16, true>(tmA, tmW, p, d.max_ctas, st)
+                           : launch2<LEMAS_EPI_GELU_TANH_F16>(tmA, tmW, p, d.max_ctas, st);
     case LEMAS_EPI_GELU_ERF_F16: return launch2<LEMAS_EPI_GELU_ERF_F16>(tmA, tmW, p, d.max_ctas, st);
-    case LEMAS_EPI_GATE_RESID_F32: return launch2<LEMAS_EPI_GATE_RESID_F32>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_GATE_RESID_F32:
+      return p.ln_out16 ? launch2<LEMAS_EPI_GATE_RESID_F32, true>(tmA, tmW, p, d.max_ctas, st)
+                        : launch2<LEMAS_EPI_GATE_RESID_F32>(tmA, tmW, p, d.max_ctas, st);
     case LEMAS_EPI_BIAS_F32: return launch2<LEMAS_EPI_BIAS_F32>(tmA, tmW, p, d.max_ctas, st);
   }
   return fail(LEMAS_ERR_INVALID, "gemm2: unsupported epilogue");

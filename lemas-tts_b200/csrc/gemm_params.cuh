@@ -15,6 +15,9 @@ struct GemmParams {
   const float* gate; int gate_bstride;
   const int* row_valid;
   const int* row_limit;   // gemm2 only: tiles starting at or beyond row_limit[batch item] are skipped
+  // LayerNorm folded into the surrounding GEMMs (gemm2 only; see lemas_gemm_desc)
+  const float* ln_scale; __half* ln_out16; int ln_ld16; float* ln_stats;
+  const float* ln_stats_in; int ln_parts; const float* ln_uv; const int* ln_step; float ln_inv_k;
   int seq_len;
   const float2* rope; int rope_cols; int inner;
   __half* vt; int vt_ld;

@@ -20,6 +20,7 @@ _lib = None
 EPI_BIAS_F16, EPI_QKV_ROPE, EPI_GELU_TANH_F16, EPI_GELU_ERF_F16, EPI_GATE_RESID_F32 = 0, 1, 2, 3, 4
 EPI_BIAS_F32, EPI_ADD_F32_F16, EPI_MISH_F16, EPI_MISH_RESID_F32 = 5, 6, 7, 8
 SAMPLE_SKIP_PADDED_ROWS = 1
+SAMPLE_FOLD_LAYERNORM = 2
 PROF_KINDS = ["preloop", "in_proj", "conv_pos", "ln_mod", "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
               "proj_out", "cfg_euler"]
 
@@ -36,6 +37,8 @@ class GemmDesc(C.Structure):
         ("resid", vp), ("ldr", i32), ("gate", vp), ("gate_bstride", i32),
         ("row_valid", vp), ("seq_len", i32), ("rope", vp), ("rope_cols", i32), ("inner", i32),
         ("vt", vp), ("vt_ld", i32), ("max_ctas", i32), ("row_limit", vp),
+        ("ln_scale", vp), ("ln_out16", vp), ("ln_ld16", i32), ("ln_stats", vp),
+        ("ln_stats_in", vp), ("ln_parts", i32), ("ln_uv", vp), ("ln_step", vp), ("ln_k", i32),
     ]
 
 

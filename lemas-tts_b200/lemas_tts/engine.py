@@ -235,7 +235,7 @@ class DiTEngine:
     def sample_loop(self, y: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor | None,
                     t_grid: torch.Tensor, cfg_strength: float, kv_len: torch.Tensor | None = None,
                     trajectory: torch.Tensor | None = None, use_graph: bool = True,
-                    skip_padded_rows: bool = False) -> torch.Tensor:
+                    skip_padded_rows: bool = False, fold_layernorm: bool = False) -> torch.Tensor:
         """The ODE loop of CFM.sample (cfm.py:382-456).  `y` [B,N,mel] fp32 is y0 on entry and is updated IN PLACE
         to the final state.  t_grid: [steps+1] fp32 (any device; read on the host, cfm.py:445-453)."""
         tg = t_grid.detach().to("cpu", f32).contiguous()
@@ -253,7 +253,8 @@ class DiTEngine:
             stage = self._traj[:n].view(trajectory.shape)
         a = self._args(y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength,
                        stage if stage is not None else trajectory, use_graph,
-                       nv.SAMPLE_SKIP_PADDED_ROWS if (skip_padded_rows and kv_len is not None) else 0)
+                       (nv.SAMPLE_SKIP_PADDED_ROWS if (skip_padded_rows and kv_len is not None) else 0)
+                       | (nv.SAMPLE_FOLD_LAYERNORM if fold_layernorm else 0))
         nv.check(nv.load().lemas_sampler_run(self._handle, C.byref(a), nv.stream()))
         if stage is not None:
             trajectory.copy_(stage)

@@ -55,7 +55,8 @@ def test_mel_strided_batch_rows():
     wav = big.cuda()[:, :7000]
     from lemas_tts import _native as nv
     fb, rng = ops.mel_filterbank()
+    fb_d, rng_d = fb.cuda(), rng.cuda()   # keep the device copies alive across the asynchronous launch
     mel = torch.empty(2, 100, 7000 // 256 + 1, device="cuda")
-    nv.check(nv.load().lemas_mel_spectrogram_1024(wav.data_ptr(), 2, 7000, wav.stride(0), nv.ptr(fb.cuda()),
-                                                  nv.ptr(rng.cuda()), 100, nv.ptr(mel), nv.stream()))
+    nv.check(nv.load().lemas_mel_spectrogram_1024(wav.data_ptr(), 2, 7000, wav.stride(0), nv.ptr(fb_d),
+                                                  nv.ptr(rng_d), 100, nv.ptr(mel), nv.stream()))
     assert (mel.cpu() - want).abs().max().item() < TOL

@@ -105,3 +105,21 @@ def test_full_nfe_c3_slice_ragged_prosody(tmp_path, skip_rows):
         full, _ = model.sample(**kw)
         assert torch.equal(out.cpu()[valid], full.cpu()[valid]), "row skipping changed a valid row"
         assert not torch.equal(out.cpu()[~valid], full.cpu()[~valid]), "nothing was skipped?"
+
+
+def test_folded_layernorm_keeps_parity(full_model):
+    """LEMAS_SAMPLE_FOLD_LAYERNORM: the LayerNorms folded into the GEMMs around them (un-normalised fp16 operand,
+    mean / rstd applied in the consumer's epilogue) against the same full-NFE reference golden and bar."""
+    case, gold = _need("full_C4_b4")
+    inp = gc.full_inputs(case)
+    kw = dict(cond=inp["cond"].cuda(), text=inp["text"].cuda(), duration=inp["duration"], steps=case["steps"],
+              cfg_strength=case["cfg"], sway_sampling_coef=case["sway"], noise=inp["noise"], use_acc_grl=False,
+              use_prosody_encoder=False, return_trajectory=False)
+    full_model.fold_layernorm = True
+    try:
+        out, _ = full_model.sample(**kw)
+    finally:
+        full_model.fold_layernorm = False
+    _check(out, gold["out"], "full_C4_b4 with folded LayerNorm")
+    plain, _ = full_model.sample(**kw)
+    assert not torch.equal(out, plain), "the folded path did not run"
