@@ -55,6 +55,9 @@ def parse():
                     help="C3 (ragged batch): also compute the padded rows that cannot reach a valid row (reference-"
                          "identical padding; default: skip them, lemas_sample_args.flags)")
     ap.add_argument("--no-c4", action="store_true", help="skip the sharded C4 block (256 utterances over the ranks)")
+    ap.add_argument("--latency-split", action="store_true",
+                    help="--gpus 2 only: add a `latency_split` block — ONE utterance of the workload with the conditional "
+                         "and unconditional forwards on the two GPUs (lemas_tts.parallel.CfgSplit) against one GPU")
     return ap.parse_args()
 
 
@@ -509,6 +512,40 @@ def run_b200(args):
                   "scaling": "strong", "seconds": ms_c4 * 1e-3, "value": gen / (ms_c4 * 1e-3), "unit": UNIT,
                   "utterances_per_rank": len(mine), "x_realtime": (gen * HOP / SR) / (ms_c4 * 1e-3)}
 
+    # SURVEY.md §8 f4, two-GPU latency mode: both ranks synthesise the SAME utterance; rank 0 runs the conditional DiT
+    # forward of every Euler step, rank 1 the unconditional one, `pred` swapped over NVLink inside one kernel per step.
+    lat = None
+    if args.latency_split:
+        if world != 2 or cfg.cfg_strength < 1e-5:
+            raise SystemExit("--latency-split needs --gpus 2 and a workload with classifier-free guidance")
+        from lemas_tts.parallel import CfgSplit
+
+        wl0 = wl if rank == 0 else Workload(args.workload, args.batch)   # rank 0's utterance on both ranks
+        c0, t0_ = wl0.cond.to(dev), wl0.text.to(dev)
+        kw0 = wl0.sample_kwargs(dev)
+
+        def one(i):
+            out, _ = model.sample(cond=c0, text=t0_, seed=5000 + i, **kw0)
+            s0, e0 = wl0.gen_slices[0]
+            return out, voc.decode(out[:, s0:e0, :].permute(0, 2, 1))
+
+        ref_out, _ = one(0)
+        ms_one, _ = timed(one, args.warmup, args.steps)
+        split = CfgSplit(dev)
+        model.cfg_split = split
+        got_out, _ = one(0)
+        same = torch.tensor([int(torch.equal(got_out, ref_out))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        ms_split, _ = timed(one, args.warmup, args.steps)
+        model.cfg_split = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        split.close()
+        lat = {"workload": wl0.describe() + " — one utterance, cond / uncond forwards on 2 GPUs, fused NVLink pred exchange",
+               "ms_one_gpu": ms_one / args.steps, "ms_two_gpus": ms_split / args.steps,
+               "speedup": ms_one / ms_split, "bit_identical_to_one_gpu": bool(same.item()),
+               "xchg_bytes_per_step_per_direction": wl0.batch * wl0.N * 128 * 4}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -584,6 +621,8 @@ def run_b200(args):
     }
     if c4 is not None:
         line["c4_sharded"] = c4
+    if lat is not None:
+        line["latency_split"] = lat
     if world == 1 and not args.no_cpu_baseline:
         info = cpu_reference_sample(wl, euler_steps=2)
         line["cpu_baseline"] = {"value": info["frames"] / info["seconds"], "unit": UNIT, "cores": info["cores"],

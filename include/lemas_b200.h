@@ -31,6 +31,13 @@ const char* lemas_last_error(void);
 int lemas_version(void);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMA kernels can run), else 0. */
 int lemas_device_supported(void);
+/* Two-GPU latency mode (lemas_sample_args.split_*): memory one process allocates and its peer process maps.
+ * lemas_peer_alloc: zero-filled memory on the current device + its 64-byte CUDA IPC handle (send it to the peer by any
+ * host channel); lemas_peer_open: map the peer's allocation for kernels of the current device (NVLink peer access). */
+int lemas_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int lemas_peer_open(const void* handle64, void** ptr);
+int lemas_peer_close(void* ptr);
+int lemas_peer_free(void* ptr);
 /* sizeof() of the ABI structs, for bindings to self-check their mirrors: 0 lemas_gemm_desc, 1 lemas_dit_config,
  * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights,
  * 7 lemas_text_block, 8 lemas_text_weights, 9 lemas_prosody_tdnn, 10 lemas_prosody_block, 11 lemas_prosody_weights;
@@ -220,6 +227,17 @@ typedef struct lemas_sample_args {
                                  from a padded row to a valid one, 30 rows per step, so rows beyond that cone can never
                                  reach a valid row of the result.  Valid rows (r < kv_len[b]) are unchanged; padded rows
                                  of the returned state then differ from the reference's (callers slice them off).     */
+  /* Two-GPU latency mode: the conditional and the unconditional forward of every Euler step
+   * (cfm.py:393-417) run on two GPUs, one process each, and swap their `pred` ([batch * seq, mel] fp32, 0.9 MB at C2)
+   * over NVLink with peer stores inside one kernel per step — no NCCL call, no host involvement, graph-replayable.
+   * All NULL = off.  This process computes variant `split_variant` (0 = conditional, 1 = unconditional: the caller then
+   * passes the dropped inputs as step_cond / text_cond) and both processes end every step with the same state y.
+   * split_xchg_local: this GPU, fp32 [2 variants][batch * seq][128]; split_flags_local: this GPU, int32 [2], zeroed once
+   * at allocation, written only by the peer; *_peer: the other process' buffers mapped through CUDA IPC.  Both
+   * processes must issue the same sequence of lemas_sampler_run calls (flags carry a call epoch). */
+  float* split_xchg_local; float* split_xchg_peer;
+  int32_t* split_flags_local; int32_t* split_flags_peer;
+  int32_t split_variant;
 } lemas_sample_args;
 #define LEMAS_SAMPLE_SKIP_PADDED_ROWS 1
 /* Fold every LayerNorm except layer 0's attn_norm and the final norm into the GEMMs around it (lemas_gemm_desc.ln_*):

@@ -1,4 +1,5 @@
 #include "common.h"
+#include <cstring>
 
 #include <atomic>
 #include <cstdlib>
@@ -111,6 +112,48 @@ int lemas_abi_sizeof(int which) {
     case 11: return (int)sizeof(lemas_prosody_weights);
   }
   return -1;
+}
+
+int lemas_peer_alloc(int64_t bytes, void** ptr, void* handle64) {
+  // zero-filled device memory of the CURRENT device plus the 64-byte CUDA IPC handle another process opens it with
+  if (!ptr || !handle64 || bytes <= 0) return lemas::fail(LEMAS_ERR_INVALID, "lemas_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    if (p) cudaFree(p);
+    return lemas::fail(LEMAS_ERR_CUDA, std::string("CUDA error: lemas_peer_alloc: ") + cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return LEMAS_OK;
+}
+
+int lemas_peer_open(const void* handle64, void** ptr) {
+  // maps the peer process's allocation for kernels of the CURRENT device (peer access over NVLink is enabled lazily)
+  if (!ptr || !handle64) return lemas::fail(LEMAS_ERR_INVALID, "lemas_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess)
+    return lemas::fail(LEMAS_ERR_CUDA, std::string("CUDA error: lemas_peer_open: ") + cudaGetErrorString(e));
+  *ptr = p;
+  return LEMAS_OK;
+}
+
+int lemas_peer_close(void* ptr) {
+  if (ptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) { (void)cudaGetLastError(); return LEMAS_ERR_CUDA; }
+  return LEMAS_OK;
+}
+
+int lemas_peer_free(void* ptr) {
+  if (ptr && cudaFree(ptr) != cudaSuccess) { (void)cudaGetLastError(); return LEMAS_ERR_CUDA; }
+  return LEMAS_OK;
 }
 
 int lemas_device_supported(void) {

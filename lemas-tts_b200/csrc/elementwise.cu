@@ -289,6 +289,59 @@ int ln_fold_pack_launch(const float* mod, long mod_w, int steps, int depth, int 
   return LEMAS_OK;
 }
 
+// Two-GPU CFG split: swap this step's `pred` with the peer GPU over NVLink (peer stores), one CTA, one kernel per step.
+//   state[2] = step, state[3] = call epoch (bit patterns);  flags[0] = "ready", flags[1] = "data", written by the PEER.
+// Protocol per step (targets grow monotonically: epoch * 4096 + step + 1, so nothing is ever reset):
+//   1. tell the peer that everything that read our exchange buffer in the previous step has finished (this kernel runs
+//      after it in stream order), i.e. it may overwrite the slot it owns here;  2. wait for the same from the peer;
+//   3. copy our variant's pred into the peer's buffer, fence, raise its data flag;  4. wait for our data flag.
+// Every wait has a deadline (a peer that died must end this process with a launch failure, not hang the GPU).
+DEVI void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+DEVI int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DEVI void split_wait(const int* flag, int target, const char* what) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < target) {
+    if (clock64() - t0 > 6000000000ll) {   // ~3 s
+      printf("lemas: two-GPU CFG split timed out waiting for the peer (%s, target %d, flag %d)\n", what, target,
+             ld_acquire_sys(flag));
+      __trap();
+    }
+    __nanosleep(64);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+cfg_split_exchange_kernel(const float* __restrict__ local, float* __restrict__ peer, long slot_floats, int variant,
+                          const float* __restrict__ state, const int* flags_local, int* flags_peer) {
+  const int step = __float_as_int(state[2]);
+  const int target = __float_as_int(state[3]) * 4096 + step + 1;
+  if (threadIdx.x == 0) {
+    st_release_sys(flags_peer + 0, target);
+    split_wait(flags_local + 0, target, "ready");
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(local + (long)variant * slot_floats);
+  float4* dst = reinterpret_cast<float4*>(peer + (long)variant * slot_floats);
+  for (long i = threadIdx.x; i < slot_floats / 4; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st_release_sys(flags_peer + 1, target);
+    split_wait(flags_local + 1, target, "data");
+  }
+}
+
+int cfg_split_exchange_launch(const float* local, float* peer, long slot_floats, int variant, const float* state,
+                              const int* flags_local, int* flags_peer, cudaStream_t st) {
+  cfg_split_exchange_kernel<<<1, 1024, 0, st>>>(local, peer, slot_floats, variant, state, flags_local, flags_peer);
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
 int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
                          long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st) {
   const long total = (long)rows * mel;

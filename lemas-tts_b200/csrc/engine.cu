@@ -17,6 +17,8 @@ int step_begin_launch(const float* mod_table, long mod_w, float* mod_cur, const 
                       cudaStream_t st);
 int cfg_euler_dev_launch(const float* pred, int ld_pred, float* y, void* x16, int ld_x16, int copies, float* traj,
                          long traj_stride, int rows, int mel, const float* state, int use_cfg, cudaStream_t st);
+int cfg_split_exchange_launch(const float* local, float* peer, long slot_floats, int variant, const float* state,
+                              const int* flags_local, int* flags_peer, cudaStream_t st);
 int ln_fold_pack_launch(const float* mod, long mod_w, int steps, int depth, int dim, void* out16, cudaStream_t st);
 
 struct Carver {
@@ -101,11 +103,12 @@ struct lemas_engine {
   struct StepGraph {
     int batch, seq, steps, variants, has_kv, flags;   // steps: the workspace carve-up (hence every captured pointer) depends on it
     float cfg;
-    const void *ws, *rope, *traj;
+    const void *ws, *rope, *traj, *split;
     cudaGraphExec_t exec;
     int nodes;
   };
   std::vector<StepGraph> graphs;
+  int split_epoch = 0;                 // two-GPU CFG split: calls so far (both processes count alike)
   cudaStream_t cap_stream = nullptr;   // capture happens on a private stream: the caller's may be the legacy default
                                        // stream, which cannot be captured; replays go to the caller's stream
 };
@@ -400,14 +403,20 @@ static int ode_step(lemas_engine* e, const DitBuffers& b, const lemas_sample_arg
   {
     PROF(LEMAS_PROF_CFG_EULER);
     LEMAS_TRY(step_begin_launch(b.mod, mod_w, b.mod_cur, b.t_dev, b.step_ctr, b.state,
-                                variants == 2 ? a->cfg_strength : 0.f, row_limit, kv2, variants * a->batch, a->seq,
+                                (variants == 2 || a->split_xchg_local) ? a->cfg_strength : 0.f, row_limit, kv2,
+                                variants * a->batch, a->seq,
                                 a->steps, st));
   }
-  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, b.pred, row_limit,
+  const bool split = a->split_xchg_local != nullptr;
+  float* pred = split ? a->split_xchg_local + (int64_t)a->split_variant * rows * 128 : b.pred;
+  LEMAS_TRY(dit_forward(e, b, a->batch, a->seq, variants, b.mod_cur, kv2, a->rope, pred, row_limit,
                         fold_ok(e, a) ? a->steps : 0, st));
   PROF(LEMAS_PROF_CFG_EULER);
-  LEMAS_TRY(cfg_euler_dev_launch(b.pred, 128, y, b.x16, 128, variants, a->trajectory, (long)rows * c.mel_dim, rows,
-                                 c.mel_dim, b.state, variants == 2 ? 1 : 0, st));
+  if (split)  // the other variant's pred arrives from the peer GPU; afterwards both slots are complete on both sides
+    LEMAS_TRY(cfg_split_exchange_launch(a->split_xchg_local, a->split_xchg_peer, (long)rows * 128, a->split_variant,
+                                        b.state, a->split_flags_local, a->split_flags_peer, st));
+  LEMAS_TRY(cfg_euler_dev_launch(split ? a->split_xchg_local : b.pred, 128, y, b.x16, 128, variants, a->trajectory,
+                                 (long)rows * c.mel_dim, rows, c.mel_dim, b.state, (variants == 2 || split) ? 1 : 0, st));
   return LEMAS_OK;
 }
 
@@ -416,7 +425,13 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   DitBuffers b;
   LEMAS_TRY(check_args(e, a, a ? a->steps : 0, &b));
   LEMAS_REQUIRE(a->steps >= 1 && a->t_grid_host, "lemas_sampler_run: steps >= 1 and a t grid are required");
-  const int variants = a->cfg_strength >= 1e-5f ? 2 : 1;
+  const bool split = a->split_xchg_local != nullptr;
+  if (split)
+    LEMAS_REQUIRE(a->cfg_strength >= 1e-5f && a->split_xchg_peer && a->split_flags_local && a->split_flags_peer &&
+                      (a->split_variant == 0 || a->split_variant == 1),
+                  "lemas_sampler_run: the two-GPU CFG split needs cfg_strength > 0, both exchange buffers and both flag "
+                  "arrays, and split_variant 0 or 1");
+  const int variants = (a->cfg_strength >= 1e-5f && !split) ? 2 : 1;   // split: ONE variant here, the other on the peer
   LEMAS_REQUIRE(variants == 1 || a->text_uncond, "lemas_sampler_run: text_uncond required when cfg_strength > 0");
   const lemas_dit_config& c = e->cfg;
   const int rows = a->batch * a->seq;
@@ -424,6 +439,10 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
   // prepare() uploaded t[0..steps-1]; the step kernels also need t[steps] for the last dt
   LEMAS_CUDA_OK(cudaMemcpyAsync(b.t_dev + a->steps, a->t_grid_host + a->steps, sizeof(float), cudaMemcpyHostToDevice, st));
   LEMAS_CUDA_OK(cudaMemsetAsync(b.step_ctr, 0, sizeof(int), st));
+  if (split) {  // state[3] = call epoch (the exchange kernel's flag targets grow monotonically across calls)
+    e->split_epoch += 1;
+    LEMAS_CUDA_OK(cudaMemcpyAsync(b.state + 3, &e->split_epoch, sizeof(int), cudaMemcpyHostToDevice, st));
+  }
   const int64_t state = (int64_t)rows * c.mel_dim;
   if (a->trajectory)
     LEMAS_CUDA_OK(cudaMemcpyAsync(a->trajectory, a->y, sizeof(float) * state, cudaMemcpyDeviceToDevice, st));
@@ -494,7 +513,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
     if (cand.batch == a->batch && cand.seq == a->seq && cand.steps == a->steps && cand.variants == variants &&
         cand.has_kv == (kv2 != nullptr) && cand.flags == a->flags &&
         cand.cfg == a->cfg_strength && cand.ws == a->workspace && cand.rope == a->rope &&
-        cand.traj == a->trajectory)
+        cand.traj == a->trajectory && cand.split == a->split_xchg_peer)
       g = &cand;
   int first_replayed = 0;
   if (!g) {
@@ -520,7 +539,7 @@ int lemas_sampler_run(lemas_engine* e, const lemas_sample_args* a, void* stream)
       e->graphs.erase(e->graphs.begin());
     }
     e->graphs.push_back({a->batch, a->seq, a->steps, variants, kv2 != nullptr, a->flags, a->cfg_strength, a->workspace, a->rope,
-                         a->trajectory, exec, nodes});
+                         a->trajectory, a->split_xchg_peer, exec, nodes});
     g = &e->graphs.back();
   }
   for (int i = first_replayed; i < a->steps; ++i) {

@@ -63,7 +63,9 @@ class SampleArgs(C.Structure):
     _fields_ = [("batch", i32), ("seq", i32), ("steps", i32), ("t_grid_host", C.POINTER(f32)),
                 ("cfg_strength", f32), ("y", vp), ("step_cond", vp), ("text_cond", vp), ("text_uncond", vp),
                 ("kv_len", vp), ("rope", vp), ("trajectory", vp), ("workspace", vp), ("workspace_bytes", i64),
-                ("use_graph", i32), ("flags", i32)]
+                ("use_graph", i32), ("flags", i32),
+                ("split_xchg_local", vp), ("split_xchg_peer", vp), ("split_flags_local", vp), ("split_flags_peer", vp),
+                ("split_variant", i32)]
 
 
 class VocosLayer(C.Structure):
@@ -111,6 +113,10 @@ SIGNATURES = {
     "lemas_last_error": (C.c_char_p, []),
     "lemas_version": (C.c_int, []),
     "lemas_device_supported": (C.c_int, []),
+    "lemas_peer_alloc": (C.c_int, [i64, C.POINTER(C.c_void_p), vp]),
+    "lemas_peer_open": (C.c_int, [vp, C.POINTER(C.c_void_p)]),
+    "lemas_peer_close": (C.c_int, [vp]),
+    "lemas_peer_free": (C.c_int, [vp]),
     "lemas_abi_sizeof": (C.c_int, [C.c_int]),
     "lemas_launch_count": (i64, []),
     "lemas_engine_profile": (C.c_int, [vp, i32]),

@@ -203,7 +203,8 @@ class DiTEngine:
             self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
         return self._ws
 
-    def _args(self, y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength, traj, use_graph, flags=0):
+    def _args(self, y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength, traj, use_graph, flags=0,
+              split=None):
         B, N, M = y.shape
         for name, t, shape in (("y", y, (B, N, self.mel_dim)), ("step_cond", step_cond, (B, N, self.mel_dim)),
                                ("text_cond", text_c, (B, N, self.text_dim))):
@@ -229,13 +230,19 @@ class DiTEngine:
         a.workspace, a.workspace_bytes = nv.ptr(ws), ws.numel()
         a.use_graph = int(use_graph)
         a.flags = int(flags)
+        if split is not None:  # two-GPU CFG split (lemas_tts.parallel.CfgSplit): this process runs ONE variant
+            if B * N > split.max_rows:
+                raise ValueError(f"CfgSplit was set up for {split.max_rows} rows, this call has {B * N}")
+            a.split_xchg_local, a.split_xchg_peer = split.xchg_ptr, split.peer_xchg_ptr
+            a.split_flags_local, a.split_flags_peer = split.flags_ptr, split.peer_flags_ptr
+            a.split_variant = int(split.variant)
         return a
 
     @nv.on_device
     def sample_loop(self, y: torch.Tensor, step_cond: torch.Tensor, text_c: torch.Tensor, text_u: torch.Tensor | None,
                     t_grid: torch.Tensor, cfg_strength: float, kv_len: torch.Tensor | None = None,
                     trajectory: torch.Tensor | None = None, use_graph: bool = True,
-                    skip_padded_rows: bool = False, fold_layernorm: bool = False) -> torch.Tensor:
+                    skip_padded_rows: bool = False, fold_layernorm: bool = False, split=None) -> torch.Tensor:
         """The ODE loop of CFM.sample (cfm.py:382-456).  `y` [B,N,mel] fp32 is y0 on entry and is updated IN PLACE
         to the final state.  t_grid: [steps+1] fp32 (any device; read on the host, cfm.py:445-453)."""
         tg = t_grid.detach().to("cpu", f32).contiguous()
@@ -254,7 +261,7 @@ class DiTEngine:
         a = self._args(y, step_cond, text_c, text_u, kv_len, steps, t_host, cfg_strength,
                        stage if stage is not None else trajectory, use_graph,
                        (nv.SAMPLE_SKIP_PADDED_ROWS if (skip_padded_rows and kv_len is not None) else 0)
-                       | (nv.SAMPLE_FOLD_LAYERNORM if fold_layernorm else 0))
+                       | (nv.SAMPLE_FOLD_LAYERNORM if fold_layernorm else 0), split=split)
         nv.check(nv.load().lemas_sampler_run(self._handle, C.byref(a), nv.stream()))
         if stage is not None:
             trajectory.copy_(stage)

@@ -101,6 +101,8 @@ class CFM(nn.Module):
         # LayerNorm folded into the surrounding GEMMs (LEMAS_SAMPLE_FOLD_LAYERNORM): same parity, 64 instead of 1 440
         # norm launches per utterance, measured 1.2 % slower on C2 -> off by default
         self.fold_layernorm = os.environ.get("LEMAS_FUSED_LN", "0") == "1"
+        # two-GPU latency mode: a lemas_tts.parallel.CfgSplit (this process then runs one CFG variant per step)
+        self.cfg_split = None
         self.use_prosody_encoder = bool(use_prosody_encoder and prosody_cfg_path and prosody_ckpt_path)
         if self.use_prosody_encoder:
             from .backbones.prosody_encoder import ProsodyEncoder
@@ -250,9 +252,16 @@ class CFM(nn.Module):
         traj = None
         if return_trajectory:
             traj = torch.empty(steps + 1, batch, max_duration, self.num_channels, device=device, dtype=torch.float32)
-        engine.sample_loop(y, step_cond, text_c, text_u if cfg_strength >= 1e-5 else None, t, cfg_strength,
-                           kv_len=kv_len, trajectory=traj, skip_padded_rows=self.skip_padded_rows and not duplicate_test,
-                           fold_layernorm=self.fold_layernorm)
+        split = self.cfg_split if cfg_strength >= 1e-5 else None
+        if split is not None and split.variant == 1:  # this process runs the unconditional forward (cfm.py:403-417)
+            engine.sample_loop(y, torch.zeros_like(step_cond), text_u, None, t, cfg_strength, kv_len=kv_len,
+                               trajectory=traj, skip_padded_rows=self.skip_padded_rows and not duplicate_test,
+                               fold_layernorm=self.fold_layernorm, split=split)
+        else:
+            engine.sample_loop(y, step_cond, text_c, text_u if (cfg_strength >= 1e-5 and split is None) else None, t,
+                               cfg_strength, kv_len=kv_len, trajectory=traj,
+                               skip_padded_rows=self.skip_padded_rows and not duplicate_test,
+                               fold_layernorm=self.fold_layernorm, split=split)
         tr.clear_cache()
 
         out = torch.where(cond_mask, cond, y)

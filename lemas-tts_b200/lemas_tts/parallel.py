@@ -146,3 +146,49 @@ def synthesize_sharded(utterances: list[dict], synth_fn, *, group=None, dst: int
     if len(merged) != len(utterances):
         raise RuntimeError(f"gather returned {len(merged)} of {len(utterances)} utterances")
     return [merged[i] for i in range(len(utterances))]
+
+
+# ------------------------------------------------------------------------------------------- two-GPU latency mode
+class CfgSplit:
+    """Two-GPU latency mode for ONE utterance: the conditional and the unconditional DiT forward of
+    every Euler step (cfm.py:393-417) run on two GPUs and swap their `pred` over NVLink inside one kernel per step
+    (`cfg_split_exchange_kernel`: peer stores + system-scope flags — no NCCL call on the data path, graph-replayable).
+
+    Two processes (ranks 0 and 1 of `group`), one GPU each, same weights, SAME `sample()` calls with the same inputs
+    and noise; rank 0 computes the conditional variant, rank 1 the unconditional one, and both return the same `out`,
+    bit-identical to the single-GPU result.  Set-up (once): each rank allocates its exchange buffer and flag words and
+    hands them to the peer through CUDA IPC (the handles travel over the process group)."""
+
+    FLAG_BYTES = 256   # flag words first (ready, data), the two pred slots behind them
+
+    def __init__(self, device, group=None, max_rows: int = 4096):
+        import ctypes as C
+
+        from . import _native as nv
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world != 2:
+            raise RuntimeError(f"CfgSplit needs exactly 2 ranks, got {world}")
+        self.variant = rank
+        self.device = torch.device(device)
+        self.max_rows = int(max_rows)
+        self._lib = nv.load()
+        own, peer, handle = C.c_void_p(), C.c_void_p(), C.create_string_buffer(64)
+        with torch.cuda.device(self.device):   # allocate here, map the peer's block for kernels of THIS device
+            nv.check(self._lib.lemas_peer_alloc(self.FLAG_BYTES + 2 * self.max_rows * 128 * 4, C.byref(own), handle))
+            both = [None, None]
+            dist.all_gather_object(both, handle.raw, group=group)
+            nv.check(self._lib.lemas_peer_open(both[1 - rank], C.byref(peer)))
+        self._own, self._peer = own.value, peer.value
+        self.flags_ptr, self.xchg_ptr = self._own, self._own + self.FLAG_BYTES
+        self.peer_flags_ptr, self.peer_xchg_ptr = self._peer, self._peer + self.FLAG_BYTES
+        dist.barrier(group)
+
+    def close(self):
+        """Both ranks call this (after their last split sample() has been synchronised)."""
+        if getattr(self, "_peer", None):
+            self._lib.lemas_peer_close(self._peer)
+            self._peer = None
+        if getattr(self, "_own", None):
+            self._lib.lemas_peer_free(self._own)
+            self._own = None

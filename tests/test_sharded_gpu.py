@@ -111,3 +111,72 @@ def test_two_ranks_nccl_bit_identical_to_one_gpu(tmp_path):
     mp.spawn(_rank_main, args=(2, 29700 + os.getpid() % 1000, str(out)), nprocs=2, join=True)
     res = torch.load(out)
     assert res["n"] == len(SHAPES) and res["same"], "sharded utterances differ from the single-GPU run"
+
+
+# ------------------------------------------------------------------------------------------- two-GPU latency mode
+def _split_main(rank, world, port, out_path):
+    import time
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from lemas_tts.model.backbones.dit import DiT
+        from lemas_tts.model.cfm import CFM
+        from lemas_tts.parallel import CfgSplit
+
+        res = {}
+        split = CfgSplit(dev)
+        for arch_name, tc, n, nt, steps in (("TINY_ARCH", 60, 300, 40, 6), ("FULL_ARCH", 937, 2187, 350, 8)):
+            arch = getattr(syn, arch_name)
+            model = CFM(transformer=DiT(**arch.to_kwargs()), mel_spec_kwargs=dict(mel_spec_type="vocos"))
+            model.load_state_dict(syn.make_dit_state_dict(arch, seed=3), strict=True)   # same seeded weights on both ranks
+            model = model.to(dev)
+            kw = dict(cond=syn.synthetic_ref_mel(1, tc, arch.mel_dim, seed=1).to(dev),
+                      text=syn.synthetic_text_ids(1, nt, arch.text_num_embeds, seed=1).to(dev), duration=n, steps=steps,
+                      cfg_strength=2.0, sway_sampling_coef=3.0, noise=syn.synthetic_noise([n], arch.mel_dim, seed=1),
+                      use_acc_grl=False, return_trajectory=False)
+            whole, _ = model.sample(**kw)                  # both CFG variants on this GPU
+            model.cfg_split = split
+            for _ in range(2):
+                got, _ = model.sample(**kw)                # one variant here, the other on the peer
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            got, _ = model.sample(**kw)
+            torch.cuda.synchronize()
+            t_split = time.perf_counter() - t0
+            model.cfg_split = None
+            t0 = time.perf_counter()
+            model.sample(**kw)
+            torch.cuda.synchronize()
+            t_whole = time.perf_counter() - t0
+            res[arch_name] = dict(same=bool(torch.equal(got, whole)), t_split=t_split, t_whole=t_whole)
+            dist.barrier()
+        if rank == 0:
+            torch.save(res, out_path)
+        # rank 1 must have produced the same state as well
+        flag = torch.tensor([int(all(v["same"] for v in res.values()))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert int(flag.item()) == 1
+        split.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_gpu_cfg_split_is_bit_identical_and_faster(tmp_path):
+    """cond / uncond forwards on two GPUs with a fused NVLink `pred` exchange per step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    out = tmp_path / "split.pt"
+    mp.spawn(_split_main, args=(2, 29800 + os.getpid() % 1000, str(out)), nprocs=2, join=True)
+    res = torch.load(out)
+    for name, r in res.items():
+        print(f"{name}: split {r['t_split'] * 1e3:.1f} ms vs one GPU {r['t_whole'] * 1e3:.1f} ms, identical {r['same']}")
+        assert r["same"], f"{name}: the two-GPU split changed the result"
