@@ -96,3 +96,28 @@ def test_prosody_conditioning_matches_reference():
         assert (traj[-1] - gold[f"last_grl{int(grl)}"]).abs().max() < TOL * 5
         assert (out - gold[f"out_grl{int(grl)}"]).abs().max() < TOL * 5
     assert (gold["out_grl0"] - gold["out_grl1"]).abs().max() > 1e-2, "the two settings must differ for the test to bite"
+
+
+def test_rotary_pair_convention_matches_an_independent_implementation():
+    """x-transformers (pinned >= 1.31.14, absent offline) rotates ADJACENT pairs (x0, x1) -> (x0 cos - x1 sin, x1 cos +
+    x0 sin) with angle n * 10000^(-2j/64) shared by columns 2j, 2j+1 (call sites: /root/reference/lemas_tts/model/
+    backbones/dit.py:236, modules.py:476-480).  GPT-J in `transformers` (installed) is an independent implementation of
+    exactly that convention (`rotate_every_two`, interleaved sin / cos): the oracle's table + rotation and the shim the
+    verbatim reference runs on (oracle/verbatim.py) must agree with it bit for bit in fp32."""
+    gptj = pytest.importorskip("transformers.models.gptj.modeling_gptj")
+    from oracle import lemas_oracle as orc
+    from oracle import verbatim
+
+    N, H, dh = 257, 4, 64
+    g = torch.Generator().manual_seed(5)
+    t = torch.randn(2, H, N, dh, generator=g)
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, dh, 2).float() / dh))
+    ang = orc.rotary_table(inv_freq, N)
+    got = orc.apply_rotary(t, ang)
+    # GPT-J layout: [batch, seq, heads, dim]; sin / cos [1, seq, dim/2]
+    half = torch.outer(torch.arange(N).float(), inv_freq)
+    want = gptj.apply_rotary_pos_emb(t.transpose(1, 2), half.sin()[None], half.cos()[None]).transpose(1, 2)
+    assert torch.equal(got, want)
+    rot = verbatim._Rotary(dh)
+    freqs, scale = rot.forward_from_seq_len(N)
+    assert torch.equal(verbatim._apply_rotary(t, freqs, scale), want)
