@@ -4,6 +4,7 @@
 
 BASELINE.json configs at the sizes and step counts they name, through the reference's own loop
 (/root/reference/lemas_tts/model/cfm.py:382-456, fp32 on the CPU, noise injected):
+  full_C1      B=1, raw 4 s reference audio (96 000 samples -> 376 frames through MelSpec), N=940, 16 steps, cfg 2, sway 5
   full_C2      B=1, N=2187 (937 reference + 1250 generated frames), 32 steps, cfg 2, sway 5
   full_C5      B=1, N=2814, edit mask False on [1125,1406), 64 steps, cfg 5, sway 3
   full_C4_b4   slice of C4: B=4, N=768 uniform (mask path cfm.py:336-339), 32 steps, cfg 2, sway 3
@@ -30,6 +31,8 @@ from oracle import verbatim  # noqa: E402
 C3_PICK = [4, 2, 0, 27]  # utterances of c3_batch(32, seed=1): durations 1673, 951, 1165, 950 (ragged, N = 1673)
 
 FULL_CASES = {
+    "full_C1": dict(kind="raw", wseed=0, seed=0, batch=1, samples=96000, ref_frames=376, frames=940, n_text=150, steps=16,
+                    cfg=2.0, sway=5.0),
     "full_C2": dict(kind="mel", wseed=0, seed=0, batch=1, ref_frames=937, frames=2187, n_text=350, steps=32, cfg=2.0,
                     sway=5.0),
     "full_C5": dict(kind="mel", wseed=0, seed=3, batch=1, ref_frames=2813, frames=2814, n_text=450, steps=64, cfg=5.0,
@@ -58,7 +61,10 @@ def full_inputs(case: dict) -> dict:
                     durations=dur.tolist())
     arch = syn.FULL_ARCH
     B, Tc, N = case["batch"], case["ref_frames"], case["frames"]
-    cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
+    if case["kind"] == "raw":   # raw reference audio: the mel front-end (modules.py:75-101) is part of the call
+        cond = syn.synthetic_ref_audio(B, case["samples"], seed=case["seed"])
+    else:
+        cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
     text = syn.synthetic_text_ids(B, case["n_text"], arch.text_num_embeds, seed=case["seed"])
     noise = syn.synthetic_noise([N] * B, arch.mel_dim, seed=case["seed"])
     edit_mask = None

@@ -77,7 +77,10 @@ def full_inputs(case: dict) -> dict:
                     durations=dur.tolist())
     arch = syn.FULL_ARCH
     B, Tc, N = case["batch"], case["ref_frames"], case["frames"]
-    cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
+    if case["kind"] == "raw":   # raw reference audio: the mel front-end (modules.py:75-101) is part of the call
+        cond = syn.synthetic_ref_audio(B, case["samples"], seed=case["seed"])
+    else:
+        cond = syn.synthetic_ref_mel(B, Tc, arch.mel_dim, seed=case["seed"])
     text = syn.synthetic_text_ids(B, case["n_text"], arch.text_num_embeds, seed=case["seed"])
     noise = syn.synthetic_noise([N] * B, arch.mel_dim, seed=case["seed"])
     edit_mask = None

@@ -2,6 +2,7 @@
 takes, against `out` minted by the VERBATIM reference loop (/root/reference/lemas_tts/model/cfm.py:382-456, fp32 CPU)
 with oracle/gen_golden_full.py:
 
+  full_C1     B=1, raw 4 s audio through the mel front-end, N=940, 16 steps (BASELINE configs[0])
   full_C2     B=1, N=2187, 32 steps          full_C5     B=1, N=2814, edit mask, 64 steps
   full_C4_b4  B=4, N=768 (slice of C4), 32   full_C3_b4  B=4 ragged, raw audio + prosody encoder (slice of C3), 32
 
@@ -50,7 +51,7 @@ def full_model():
     return model.cuda()
 
 
-@pytest.mark.parametrize("name", ["full_C2", "full_C5", "full_C4_b4"])
+@pytest.mark.parametrize("name", ["full_C1", "full_C2", "full_C5", "full_C4_b4"])
 @pytest.mark.parametrize("trajectory", [False, True])
 def test_full_nfe_matches_reference(full_model, name, trajectory):
     case, gold = _need(name)
