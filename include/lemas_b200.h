@@ -40,8 +40,8 @@ int lemas_peer_close(void* ptr);
 int lemas_peer_free(void* ptr);
 /* sizeof() of the ABI structs, for bindings to self-check their mirrors: 0 lemas_gemm_desc, 1 lemas_dit_config,
  * 2 lemas_dit_layer, 3 lemas_dit_weights, 4 lemas_sample_args, 5 lemas_vocos_layer, 6 lemas_vocos_weights,
- * 7 lemas_text_block, 8 lemas_text_weights, 9 lemas_prosody_tdnn, 10 lemas_prosody_block, 11 lemas_prosody_weights;
- * else -1. */
+ * 7 lemas_text_block, 8 lemas_text_weights, 9 lemas_prosody_tdnn, 10 lemas_prosody_block, 11 lemas_prosody_weights,
+ * 12 lemas_bigvgan_block, 13 lemas_bigvgan_stage, 14 lemas_bigvgan_weights; else -1. */
 int lemas_abi_sizeof(int which);
 /* Number of kernels this library has launched in the calling process since it was loaded (all entry points). */
 int64_t lemas_launch_count(void);
@@ -104,6 +104,8 @@ typedef struct lemas_gemm_desc {
    * *ln_step - 1.  Algebraically LayerNorm(x) (1 + scale) + shift fed to the same GEMM (modules.py:314, 637). */
   const float* ln_scale; void* ln_out16; int32_t ln_ld16; float* ln_stats;
   const float* ln_stats_in; int32_t ln_parts; const float* ln_uv; const int32_t* ln_step; int32_t ln_k;
+  int32_t tap_dilation;      /* taps > 1: rows are shifted by (tap - tap_pad) * tap_dilation (dilated convolution);
+                                0 means 1                                                                          */
 } lemas_gemm_desc;
 
 int lemas_gemm_f16(const lemas_gemm_desc* d, void* stream);
@@ -296,6 +298,42 @@ int64_t lemas_vocos_workspace_bytes(const lemas_vocos_weights* w, int32_t batch,
 /* Vocos.decode (utils_infer.py:549): mel fp32 [batch, in_ch, t] -> wav fp32 [batch, (t-1)*256]. */
 int lemas_vocos_decode(const lemas_vocos_weights* w, const float* mel, float* wav, int32_t batch, int32_t t,
                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BigVGAN-v2 generator — the reference's `mel_spec_type: bigvgan` vocoder branch (utils_infer.py:144-158 builds
+ * `bigvgan.BigVGAN.from_pretrained("nvidia/bigvgan_v2_24khz_100band_256x", use_cuda_kernel=False)` from the un-vendored
+ * third_party/BigVGAN submodule; utils_infer.py:550-551 calls `vocoder(mel)`).  Replaces BigVGAN.forward.
+ * All activations are time-major [batch, T, Cpad], Cpad = channels rounded up to a multiple of 64, padded channels zero.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct lemas_bigvgan_block {      /* one AMPBlock1: x += conv2_d(act(conv1_d(act(x)))) for 3 dilations          */
+  int32_t kernel;                         /* odd kernel size (3, 7, 11)                                                 */
+  int32_t dilation[3];                    /* of convs1 (convs2 have dilation 1)                                         */
+  const void* w1[3]; const float* b1[3];  /* fp16 tap-major [kernel * Cpad, Cpad] (row = tap * Cpad + out), fp32 [Cpad]  */
+  const void* w2[3]; const float* b2[3];
+  const float* act[6];                    /* fp32 [2, Cpad]: e^alpha | 1 / (e^beta + 1e-9)   (activations.{0..5})        */
+} lemas_bigvgan_block;
+
+typedef struct lemas_bigvgan_stage {
+  int32_t rate, ch_in, ch_out;            /* up-sampling rate r; padded channel counts                                   */
+  const void* up_w; const float* up_b;    /* ConvTranspose1d(k 2r, stride r, pad r/2) as a 3-tap GEMM: fp16 [3 * r * ch_out,
+                                             ch_in], row = tap * r * ch_out + phase * ch_out + out (tap 0, 1, 2 = input row
+                                             m-1, m, m+1; unused (tap, phase) blocks zero); bias fp32 [r * ch_out]          */
+  lemas_bigvgan_block block[3];
+} lemas_bigvgan_stage;
+
+typedef struct lemas_bigvgan_weights {
+  int32_t num_mels, ch0, stages, use_tanh;
+  const void* pre_w; const float* pre_b;  /* conv_pre: fp16 tap-major [7 * ch0, 128], fp32 [ch0]                          */
+  const lemas_bigvgan_stage* stage;       /* host array [stages]                                                         */
+  const float* post_act;                  /* activation_post: fp32 [2, Cpad_last]                                         */
+  const float* post_w; float post_bias;   /* conv_post: fp32 [7, Cpad_last] tap-major; bias (0 when use_bias_at_final = 0) */
+  float aa_filter[12];                    /* Kaiser-sinc low-pass of the anti-aliased activations (cutoff 0.25, hw 0.3)   */
+} lemas_bigvgan_weights;
+
+int64_t lemas_bigvgan_workspace_bytes(const lemas_bigvgan_weights* w, int32_t batch, int32_t t);
+/* mel fp32 [batch, num_mels, t] -> wav fp32 [batch, t * prod(rate)]. */
+int lemas_bigvgan_decode(const lemas_bigvgan_weights* w, const float* mel, float* wav, int32_t batch, int32_t t,
+                         void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Text embedding (dit.py:51-81 TextEmbedding.forward + ConvNeXtV2Block modules.py:241-269 + GRN modules.py:225-234):

@@ -110,6 +110,9 @@ int lemas_abi_sizeof(int which) {
     case 9: return (int)sizeof(lemas_prosody_tdnn);
     case 10: return (int)sizeof(lemas_prosody_block);
     case 11: return (int)sizeof(lemas_prosody_weights);
+    case 12: return (int)sizeof(lemas_bigvgan_block);
+    case 13: return (int)sizeof(lemas_bigvgan_stage);
+    case 14: return (int)sizeof(lemas_bigvgan_weights);
   }
   return -1;
 }

@@ -211,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(empty_bar + stage, phase ^ 1);
           mbar_arrive_expect_tx(full_bar + stage, S::STAGE_BYTES);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          tma_load_3d(sa, &tmA, full_bar + stage, a_col0 + kc * BLOCK_K, row0 + tap - p.tap_pad, b);
+          tma_load_3d(sa, &tmA, full_bar + stage, a_col0 + kc * BLOCK_K, row0 + (tap - p.tap_pad) * p.tap_dil, b);
           tma_load_2d(sa + S::A_BYTES, &tmW, full_bar + stage, kc * BLOCK_K, tap * p.w_tap_stride + n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -344,6 +344,7 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   p.kc_per_tap = d.k_per_tap / BLOCK_K;
   p.k_iters = p.kc_per_tap * d.taps;
   p.tap_pad = d.tap_pad; p.w_tap_stride = d.w_tap_stride; p.group_cols = d.group_cols;
+  p.tap_dil = d.tap_dilation > 0 ? d.tap_dilation : 1;
   p.bias = d.bias;
   p.out16 = static_cast<__half*>(d.out16); p.ld16 = d.ld16;
   p.out32 = d.out32; p.ld32 = d.ld32;

@@ -7,7 +7,7 @@ namespace lemas {
 
 struct GemmParams {
   int batches, rows;      // A tiling: tiles never straddle a batch item
-  int n, k_iters, kc_per_tap, tap_pad, w_tap_stride, group_cols;
+  int n, k_iters, kc_per_tap, tap_pad, w_tap_stride, group_cols, tap_dil;
   const float* bias;
   __half* out16; int ld16;
   float* out32; int ld32;

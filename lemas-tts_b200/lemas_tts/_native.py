@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("vt", vp), ("vt_ld", i32), ("max_ctas", i32), ("row_limit", vp),
         ("ln_scale", vp), ("ln_out16", vp), ("ln_ld16", i32), ("ln_stats", vp),
         ("ln_stats_in", vp), ("ln_parts", i32), ("ln_uv", vp), ("ln_step", vp), ("ln_k", i32),
+        ("tap_dilation", i32),
     ]
 
 
@@ -108,6 +109,21 @@ class ProsodyWeights(C.Structure):
                 ("asp_norm_b", vp), ("fc_w", vp), ("fc_b", vp)]
 
 
+class BigvganBlock(C.Structure):
+    _fields_ = [("kernel", i32), ("dilation", i32 * 3), ("w1", vp * 3), ("b1", vp * 3), ("w2", vp * 3), ("b2", vp * 3),
+                ("act", vp * 6)]
+
+
+class BigvganStage(C.Structure):
+    _fields_ = [("rate", i32), ("ch_in", i32), ("ch_out", i32), ("up_w", vp), ("up_b", vp), ("block", BigvganBlock * 3)]
+
+
+class BigvganWeights(C.Structure):
+    _fields_ = [("num_mels", i32), ("ch0", i32), ("stages", i32), ("use_tanh", i32), ("pre_w", vp), ("pre_b", vp),
+                ("stage", C.POINTER(BigvganStage)), ("post_act", vp), ("post_w", vp), ("post_bias", f32),
+                ("aa_filter", f32 * 12)]
+
+
 # every symbol include/lemas_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "lemas_last_error": (C.c_char_p, []),
@@ -149,6 +165,8 @@ SIGNATURES = {
     "lemas_dit_forward": (C.c_int, [vp, C.POINTER(SampleArgs), f32, vp, vp, vp]),
     "lemas_vocos_workspace_bytes": (i64, [C.POINTER(VocosWeights), i32, i32]),
     "lemas_vocos_decode": (C.c_int, [C.POINTER(VocosWeights), vp, vp, i32, i32, vp, i64, vp]),
+    "lemas_bigvgan_workspace_bytes": (i64, [C.POINTER(BigvganWeights), i32, i32]),
+    "lemas_bigvgan_decode": (C.c_int, [C.POINTER(BigvganWeights), vp, vp, i32, i32, vp, i64, vp]),
     "lemas_text_workspace_bytes": (i64, [C.POINTER(TextWeights), i32, i32]),
     "lemas_text_embedding": (C.c_int, [C.POINTER(TextWeights), vp, vp, vp, i32, i32, vp, i64, vp]),
 }

@@ -435,3 +435,163 @@ class TextEngine:
         nv.check(nv.load().lemas_text_embedding(C.byref(self._weights), nv.ptr(ids), nv.ptr(drop), nv.ptr(out), B, N,
                                                 nv.ptr(self._ws), self._ws.numel(), nv.stream()))
         return out
+
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def bigvgan_aa_filter() -> torch.Tensor:
+    """Kaiser-windowed sinc low-pass of BigVGAN's anti-aliased activations (alias_free_activation/torch/filter.py,
+    kaiser_sinc_filter1d(cutoff=0.25, half_width=0.3, kernel_size=12)); fp32, unit DC gain."""
+    import math
+
+    k, cutoff, half_width = 12, 0.25, 0.3
+    half = k // 2
+    A = 2.285 * (half - 1) * math.pi * (4 * half_width) + 7.95
+    beta = 0.1102 * (A - 8.7) if A > 50.0 else (0.5842 * (A - 21) ** 0.4 + 0.07886 * (A - 21.0) if A >= 21.0 else 0.0)
+    window = torch.kaiser_window(k, beta=beta, periodic=False)
+    time = torch.arange(-half, half) + 0.5
+    f = 2 * cutoff * window * torch.sinc(2 * cutoff * time)
+    return (f / f.sum()).float()
+
+
+def bigvgan_pack_conv(wt: torch.Tensor, cin_pad: int, cout_pad: int) -> torch.Tensor:
+    """Conv1d weight [cout, cin, k] -> tap-major GEMM operand [k * cout_pad, cin_pad] (row = tap * cout_pad + out)."""
+    cout, cin, k = wt.shape
+    p = torch.zeros(k, cout_pad, cin_pad)
+    p[:, :cout, :cin] = wt.float().permute(2, 0, 1)
+    return p.reshape(k * cout_pad, cin_pad)
+
+
+def bigvgan_pack_upsample(up: torch.Tensor, r: int, cin_pad: int, cout_pad: int) -> torch.Tensor:
+    """ConvTranspose1d weight [cin, cout, 2r] (stride r, padding r/2) -> 3-tap GEMM operand [3 * r * cout_pad, cin_pad].
+    Output sample m*r + ph takes input row m + delta (tap 0, 1, 2 = delta -1, 0, +1) through kernel index
+    ph + r/2 - delta*r when that lies in [0, 2r); the other (tap, phase) blocks stay zero."""
+    cin, cout, k = up.shape
+    assert k == 2 * r and r % 2 == 0
+    p = torch.zeros(3, r, cout_pad, cin_pad)
+    for tap, delta in enumerate((-1, 0, 1)):
+        for ph in range(r):
+            kk = ph + r // 2 - delta * r
+            if 0 <= kk < 2 * r:
+                p[tap, ph, :cout, :cin] = up[:, :, kk].float().t()
+    return p.reshape(3 * r * cout_pad, cin_pad)
+
+
+class BigVGANEngine:
+    """Packed BigVGAN-v2 weights (state dict after remove_weight_norm, NVIDIA/BigVGAN key layout) +
+    `lemas_bigvgan_decode`.  Convolutions become tap-major fp16 GEMM operands on channel counts padded to 64;
+    transposed convolutions become 3-tap GEMMs over (phase, channel) columns (csrc/bigvgan.cu)."""
+
+    def __init__(self, sd: dict, h: dict, device="cuda"):
+        nv.require_device()
+        self.device = dv = torch.device(device)
+        keep = self._keep = []
+
+        def hold(t):
+            keep.append(t)
+            return t
+
+        rates, up_k = list(h["upsample_rates"]), list(h["upsample_kernel_sizes"])
+        rb_k, rb_d = list(h["resblock_kernel_sizes"]), [list(d) for d in h["resblock_dilation_sizes"]]
+        if len(rb_k) != 3 or any(len(d) != 3 for d in rb_d) or str(h.get("resblock", "1")) != "1":
+            raise ValueError("lemas_b200: the native BigVGAN is built for resblock '1' with 3 kernel sizes x 3 dilations")
+        if h.get("activation", "snakebeta") != "snakebeta":
+            raise ValueError("lemas_b200: only the 'snakebeta' activation of bigvgan_v2 is built")
+        if any(k != 2 * r or r % 2 for r, k in zip(rates, up_k)):
+            raise ValueError("lemas_b200: up-sampling layers must have kernel = 2 * rate and an even rate")
+        logscale = bool(h.get("snake_logscale", True))
+        self.num_mels = int(h["num_mels"])
+        self.total_up = 1
+        for r in rates:
+            self.total_up *= r
+        ch0 = int(h["upsample_initial_channel"])
+        if ch0 % 64:
+            raise ValueError("lemas_b200: upsample_initial_channel must be a multiple of 64")
+
+        def conv_pack(wt, cin_pad, cout_pad):
+            return nv.ptr(hold(_dev(bigvgan_pack_conv(wt, cin_pad, cout_pad), dv, f16)))
+
+        def vec_pack(v, n_pad):
+            p = torch.zeros(n_pad)
+            p[: v.numel()] = v.float()
+            return nv.ptr(hold(_dev(p, dv, f32)))
+
+        def act_pack(prefix, c_pad):                   # [2, c_pad]: e^alpha | 1 / (e^beta + 1e-9); padded channels 0
+            a, b = sd[prefix + "alpha"].float(), sd[prefix + "beta"].float()
+            if logscale:
+                a, b = a.exp(), b.exp()
+            p = torch.zeros(2, c_pad)
+            p[0, : a.numel()] = a
+            p[1, : b.numel()] = 1.0 / (b + 1e-9)
+            return nv.ptr(hold(_dev(p, dv, f32)))
+
+        w = nv.BigvganWeights()
+        w.num_mels, w.ch0, w.stages = self.num_mels, ch0, len(rates)
+        w.use_tanh = 1 if h.get("use_tanh_at_final", True) else 0
+        pre = sd["conv_pre.weight"]
+        if tuple(pre.shape) != (ch0, self.num_mels, 7) or self.num_mels > 128:
+            raise ValueError(f"lemas_b200: conv_pre.weight {tuple(pre.shape)} does not match the config")
+        w.pre_w = conv_pack(pre, 128, ch0)
+        w.pre_b = vec_pack(sd["conv_pre.bias"], ch0)
+        stages = (nv.BigvganStage * len(rates))()
+        cin, cin_pad = ch0, ch0
+        for i, r in enumerate(rates):
+            cout = cin // 2
+            cpad = _pad64(cout)
+            S = stages[i]
+            S.rate, S.ch_in, S.ch_out = r, cin_pad, cpad
+            up = sd[f"ups.{i}.0.weight"].float()        # ConvTranspose1d weight [cin, cout, 2r]
+            if tuple(up.shape) != (cin, cout, 2 * r):
+                raise ValueError(f"lemas_b200: ups.{i}.0.weight {tuple(up.shape)} does not match the config")
+            S.up_w = nv.ptr(hold(_dev(bigvgan_pack_upsample(up, r, cin_pad, cpad), dv, f16)))
+            ub = torch.zeros(r, cpad)
+            ub[:, :cout] = sd[f"ups.{i}.0.bias"].float()[None, :]
+            S.up_b = nv.ptr(hold(_dev(ub.reshape(-1), dv, f32)))
+            for j in range(3):
+                q = f"resblocks.{i * 3 + j}."
+                K = S.block[j]
+                K.kernel = int(rb_k[j])
+                for d in range(3):
+                    K.dilation[d] = int(rb_d[j][d])
+                    K.w1[d] = conv_pack(sd[f"{q}convs1.{d}.weight"], cpad, cpad)
+                    K.b1[d] = vec_pack(sd[f"{q}convs1.{d}.bias"], cpad)
+                    K.w2[d] = conv_pack(sd[f"{q}convs2.{d}.weight"], cpad, cpad)
+                    K.b2[d] = vec_pack(sd[f"{q}convs2.{d}.bias"], cpad)
+                for a in range(6):
+                    K.act[a] = act_pack(f"{q}activations.{a}.act.", cpad)
+            cin, cin_pad = cout, cpad
+        self._stages = stages
+        w.stage = stages
+        w.post_act = act_pack("activation_post.act.", cin_pad)
+        post = sd["conv_post.weight"].float()           # [1, cin, 7]
+        if tuple(post.shape) != (1, cin, 7):
+            raise ValueError(f"lemas_b200: conv_post.weight {tuple(post.shape)} does not match the config")
+        pw = torch.zeros(7, cin_pad)
+        pw[:, :cin] = post[0].t()
+        w.post_w = nv.ptr(hold(_dev(pw, dv, f32)))
+        pb = sd.get("conv_post.bias")
+        w.post_bias = float(pb.float().item()) if pb is not None else 0.0
+        for i, v in enumerate(bigvgan_aa_filter().tolist()):
+            w.aa_filter[i] = v
+        self._weights = w
+        self._ws = None
+
+    @nv.on_device
+    def decode(self, mel: torch.Tensor) -> torch.Tensor:
+        """BigVGAN.forward (utils_infer.py:550-551): mel [B, num_mels, T] -> wav [B, 1, T * prod(rates)] fp32."""
+        if mel.dim() != 3 or mel.shape[1] != self.num_mels:
+            raise ValueError(f"mel: expected [B, {self.num_mels}, T], got {tuple(mel.shape)}")
+        mel = mel.to(device=self.device, dtype=f32).contiguous()
+        B, _, T = mel.shape
+        if T < 1:
+            raise ValueError("bigvgan needs at least 1 frame")
+        need = int(nv.load().lemas_bigvgan_workspace_bytes(C.byref(self._weights), B, T))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        wav = torch.empty(B, 1, T * self.total_up, device=self.device, dtype=f32)
+        nv.check(nv.load().lemas_bigvgan_decode(C.byref(self._weights), nv.ptr(mel), nv.ptr(wav), B, T,
+                                                nv.ptr(self._ws), self._ws.numel(), nv.stream()))
+        return wav

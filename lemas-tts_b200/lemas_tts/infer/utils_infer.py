@@ -116,10 +116,22 @@ def chunk_text(text, max_chars=135):
 
 
 def load_vocoder(vocoder_name="vocos", is_local=False, local_path="", device=device, hf_cache_dir=None):
-    """utils_infer.py:120-159.  Returns an object with `.decode(mel[B,100,T]) -> wav[B,S]`."""
+    """utils_infer.py:120-159.  vocos: an object with `.decode(mel[B,100,T]) -> wav[B,S]`; bigvgan: a callable
+    `vocoder(mel[B,100,T]) -> wav[B,1,S]`."""
+    if vocoder_name == "bigvgan":
+        # utils_infer.py:144-158: BigVGAN.from_pretrained(local dir | hub id), remove_weight_norm, eval, to(device);
+        # the un-vendored third_party/BigVGAN class is replaced by lemas_tts.bigvgan.BigVGAN (same surface)
+        from lemas_tts.bigvgan import BigVGAN
+
+        if is_local:
+            vocoder = BigVGAN.from_pretrained(local_path, use_cuda_kernel=False)
+        else:
+            vocoder = BigVGAN.from_pretrained("nvidia/bigvgan_v2_24khz_100band_256x", use_cuda_kernel=False,
+                                              cache_dir=hf_cache_dir)
+        vocoder.remove_weight_norm()
+        return vocoder.eval().to(device)
     if vocoder_name != "vocos":
-        raise ImportError("vocoder 'bigvgan' needs third_party/BigVGAN, which the reference does not vendor "
-                          "(utils_infer.py:144-158); both shipped configs use vocos")
+        raise ValueError(f"unknown vocoder {vocoder_name!r} (vocos | bigvgan)")
     if is_local:
         print(f"Load vocos from local path {local_path}")
         config_path = f"{local_path}/config.yaml"

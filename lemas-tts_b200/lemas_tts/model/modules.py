@@ -47,6 +47,35 @@ def get_vocos_mel_spectrogram(waveform, n_fft=1024, n_mel_channels=100, target_s
     return tf(waveform.float()).clamp(min=1e-5).log()
 
 
+def slaney_mel_filterbank(sample_rate: int, n_fft: int, n_mels: int, fmin: float = 0.0, fmax=None) -> torch.Tensor:
+    """What `librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)` returns with its defaults (Slaney mel scale, unit-area
+    triangles): [n_mels, n_fft // 2 + 1].  librosa is not a dependency here; torchaudio implements the same filterbank."""
+    fmax = sample_rate / 2.0 if fmax is None else float(fmax)
+    fb = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, float(fmin), fmax, n_mels, sample_rate, norm="slaney",
+                                               mel_scale="slaney")
+    return fb.t().contiguous()
+
+
+def get_bigvgan_mel_spectrogram(waveform, n_fft=1024, n_mel_channels=100, target_sample_rate=24000, hop_length=256,
+                                win_length=1024, fmin=0, fmax=None, center=False):
+    """modules.py:30-72 (the `mel_spec_type: bigvgan` front-end): reflect-pad (n_fft - hop) / 2, STFT without centering,
+    sqrt(re^2 + im^2 + 1e-9), Slaney mel filterbank, log(clamp 1e-5).  Runs on the waveform's device."""
+    if waveform.dim() == 3:
+        waveform = waveform.squeeze(1)
+    assert waveform.dim() == 2
+    key = ("bigvgan", str(waveform.device), n_fft, n_mel_channels, target_sample_rate, hop_length, win_length, fmin, fmax)
+    if key not in _MEL_CACHE:
+        _MEL_CACHE[key] = (slaney_mel_filterbank(target_sample_rate, n_fft, n_mel_channels, fmin, fmax).to(waveform.device),
+                           torch.hann_window(win_length, device=waveform.device))
+    mel_basis, window = _MEL_CACHE[key]
+    pad = (n_fft - hop_length) // 2
+    x = F.pad(waveform.float().unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    spec = torch.stft(x, n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    mag = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-9)
+    return torch.log(torch.clamp(torch.matmul(mel_basis, mag), min=1e-5))
+
+
 class MelSpec(nn.Module):
     """modules.py:104-143."""
 
@@ -54,12 +83,9 @@ class MelSpec(nn.Module):
                  mel_spec_type="vocos"):
         super().__init__()
         assert mel_spec_type in ["vocos", "bigvgan"], "We only support two extract mel backend: vocos or bigvgan"
-        if mel_spec_type == "bigvgan":
-            raise ImportError("mel_spec_type='bigvgan' needs third_party/BigVGAN, which the reference does not vendor "
-                              "(utils_infer.py:144-158); both shipped configs use vocos")
         self.n_fft, self.hop_length, self.win_length = n_fft, hop_length, win_length
         self.n_mel_channels, self.target_sample_rate = n_mel_channels, target_sample_rate
-        self.extractor = get_vocos_mel_spectrogram
+        self.extractor = get_vocos_mel_spectrogram if mel_spec_type == "vocos" else get_bigvgan_mel_spectrogram
         self.register_buffer("dummy", torch.tensor(0), persistent=False)
 
     def forward(self, wav):

@@ -23,7 +23,8 @@ def _chk(t: torch.Tensor, dtype, name: str):
 def gemm(a16: torch.Tensor, w16: torch.Tensor, *, epilogue: int, n: int | None = None, bias=None, block_n: int = 128,
          out16=None, out32=None, resid=None, gate=None, gate_bstride: int = 0, row_valid=None, seq_len: int | None = None,
          rope=None, rope_cols: int = 0, inner: int = 0, vt=None, taps: int = 1, tap_pad: int = 0,
-         w_tap_stride: int = 0, group_cols: int = 0, k_per_tap: int | None = None, max_ctas: int = 0):
+         w_tap_stride: int = 0, group_cols: int = 0, k_per_tap: int | None = None, max_ctas: int = 0,
+         tap_dilation: int = 1):
     """acc = A · Wᵀ with a fused epilogue.  a16: [rows, K] or [batches, rows, K] fp16; w16: [w_rows, ldw] fp16."""
     nv.require_device()
     _chk(a16, f16, "a16")
@@ -53,6 +54,7 @@ def gemm(a16: torch.Tensor, w16: torch.Tensor, *, epilogue: int, n: int | None =
     if vt is not None:
         d.vt, d.vt_ld = nv.ptr(vt), vt.shape[-1]
     d.max_ctas = max_ctas
+    d.tap_dilation = tap_dilation
     nv.check(nv.load().lemas_gemm_f16(d, nv.stream()))
 
 

@@ -163,6 +163,67 @@ def make_vocos_state_dict(arch: VocosArch = FULL_VOCOS, seed: int = 7) -> dict[s
     return sd
 
 
+@dataclass
+class BigVGANArch:
+    """config.json of nvidia/bigvgan_v2_24khz_100band_256x (the model utils_infer.py:150-155 names)."""
+
+    num_mels: int = 100
+    upsample_rates: tuple = (4, 4, 2, 2, 2, 2)
+    upsample_kernel_sizes: tuple = (8, 8, 4, 4, 4, 4)
+    upsample_initial_channel: int = 1536
+    resblock_kernel_sizes: tuple = (3, 7, 11)
+    resblock_dilation_sizes: tuple = ((1, 3, 5), (1, 3, 5), (1, 3, 5))
+    snake_logscale: bool = True
+    use_bias_at_final: bool = False
+    use_tanh_at_final: bool = False
+
+    def to_config(self) -> dict:
+        return dict(num_mels=self.num_mels, upsample_rates=list(self.upsample_rates),
+                    upsample_kernel_sizes=list(self.upsample_kernel_sizes),
+                    upsample_initial_channel=self.upsample_initial_channel, resblock="1",
+                    resblock_kernel_sizes=list(self.resblock_kernel_sizes),
+                    resblock_dilation_sizes=[list(d) for d in self.resblock_dilation_sizes], activation="snakebeta",
+                    snake_logscale=self.snake_logscale, use_bias_at_final=self.use_bias_at_final,
+                    use_tanh_at_final=self.use_tanh_at_final, sampling_rate=24000, n_fft=1024, hop_size=256,
+                    win_size=1024, fmin=0, fmax=None)
+
+
+FULL_BIGVGAN = BigVGANArch()
+# 128 -> 64 -> 32 channels (the last stage exercises the channel padding to 64), total up-sampling 8x
+TINY_BIGVGAN = BigVGANArch(upsample_rates=(4, 2), upsample_kernel_sizes=(8, 4), upsample_initial_channel=128)
+
+
+def make_bigvgan_state_dict(arch: BigVGANArch = FULL_BIGVGAN, seed: int = 17) -> dict[str, torch.Tensor]:
+    """State dict in the key layout of `bigvgan_generator.pt["generator"]` after remove_weight_norm()."""
+    g = _gen(seed)
+    sd: dict[str, torch.Tensor] = {}
+    ch = arch.upsample_initial_channel
+    sd["conv_pre.weight"] = _normal(g, (ch, arch.num_mels, 7), 0.25 / math.sqrt(7 * arch.num_mels))
+    sd["conv_pre.bias"] = _normal(g, (ch,), 0.02)
+    n = 0
+    for i, (r, k) in enumerate(zip(arch.upsample_rates, arch.upsample_kernel_sizes)):
+        sd[f"ups.{i}.0.weight"] = _normal(g, (ch, ch // 2, k), 1.0 / math.sqrt(2 * ch))
+        sd[f"ups.{i}.0.bias"] = _normal(g, (ch // 2,), 0.02)
+        ch //= 2
+        for kk in arch.resblock_kernel_sizes:
+            q = f"resblocks.{n}."
+            for d in range(3):
+                sd[f"{q}convs1.{d}.weight"] = _normal(g, (ch, ch, kk), 1.0 / math.sqrt(ch * kk))
+                sd[f"{q}convs1.{d}.bias"] = _normal(g, (ch,), 0.02)
+                sd[f"{q}convs2.{d}.weight"] = _normal(g, (ch, ch, kk), 0.4 / math.sqrt(ch * kk))
+                sd[f"{q}convs2.{d}.bias"] = _normal(g, (ch,), 0.02)
+            for a in range(6):
+                sd[f"{q}activations.{a}.act.alpha"] = _normal(g, (ch,), 0.3)
+                sd[f"{q}activations.{a}.act.beta"] = _normal(g, (ch,), 0.3)
+            n += 1
+    sd["activation_post.act.alpha"] = _normal(g, (ch,), 0.3)
+    sd["activation_post.act.beta"] = _normal(g, (ch,), 0.3)
+    sd["conv_post.weight"] = _normal(g, (1, ch, 7), 0.25 / math.sqrt(7 * ch))
+    if arch.use_bias_at_final:
+        sd["conv_post.bias"] = _normal(g, (1,), 0.02)
+    return sd
+
+
 # ----------------------------------------------------------------------------- inputs
 
 

@@ -11,7 +11,8 @@ un-vendored third-party modules the model files import are replaced by restateme
 
 * torchdiffeq.odeint            — fixed-grid Euler (torchdiffeq 0.2.4, requirements.txt:167)
 * x_transformers.x_transformers — RotaryEmbedding / apply_rotary_pos_emb (>=1.31.14, requirements.txt:180)
-* librosa.filters, jieba, pypinyin — import-only stubs (bigvgan mel / pinyin paths are never taken)
+* librosa.filters.mel — the Slaney filterbank restated in oracle/bigvgan_oracle.py (bigvgan mel front-end only)
+* jieba, pypinyin — import-only stubs (pinyin paths are never taken)
 """
 from __future__ import annotations
 
@@ -112,7 +113,13 @@ def install() -> None:
     xt.x_transformers = stub("x_transformers.x_transformers", RotaryEmbedding=_Rotary,
                              apply_rotary_pos_emb=_apply_rotary)
     lib = stub("librosa")
-    lib.filters = stub("librosa.filters", mel=lambda **kw: (_ for _ in ()).throw(NotImplementedError()))
+    def _librosa_mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None, **kw):
+        # librosa.filters.mel with its defaults (Slaney scale, Slaney norm), restated in oracle/bigvgan_oracle.py
+        from oracle.bigvgan_oracle import slaney_mel_filterbank
+
+        return slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax).numpy()
+
+    lib.filters = stub("librosa.filters", mel=_librosa_mel)
     stub("jieba")
     stub("pypinyin", lazy_pinyin=None, Style=None)
 

@@ -35,7 +35,7 @@ def test_ctypes_structs_match_c_layout():
     lib = nv.load()
     for idx, cls in enumerate([nv.GemmDesc, nv.DitConfig, nv.DitLayer, nv.DitWeights, nv.SampleArgs, nv.VocosLayer,
                                nv.VocosWeights, nv.TextBlock, nv.TextWeights, nv.ProsodyTdnn, nv.ProsodyBlock,
-                               nv.ProsodyWeights]):
+                               nv.ProsodyWeights, nv.BigvganBlock, nv.BigvganStage, nv.BigvganWeights]):
         assert lib.lemas_abi_sizeof(idx) == C.sizeof(cls), cls.__name__
 
 
