@@ -23,11 +23,9 @@ namespace lemas {
 
 int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream);
 
-constexpr int AA_TT = 48;          // output rows per tile
-constexpr int AA_CH = 64;          // channels per tile
-constexpr int AA_XR = AA_TT + 12;  // x rows staged: [t0 - 6, t0 + TT + 5]
-constexpr int AA_SR = 2 * AA_TT + 10;  // 2x-rate samples staged: n in [2 t0 - 5, 2 t0 + 2 TT + 4]
-constexpr int AA_THREADS = 256;
+constexpr int AA_L = 30;           // outputs per thread (one channel, consecutive rows); AA_L + 6 is a multiple of 6
+constexpr int AA_CH = 64;          // channels per block (consecutive threads = consecutive channels: coalesced rows)
+constexpr int AA_THREADS = 256;    // 4 time chunks x 64 channels
 
 struct AaFilter { float f[12]; };
 
@@ -35,60 +33,100 @@ template <typename T> DEVI float ld_as_float(const T* p);
 template <> DEVI float ld_as_float<float>(const float* p) { return *p; }
 template <> DEVI float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
 
+// SnakeBeta with precomputed e^alpha (ea) and 1 / (e^beta + 1e-9) (ib):  u + ib sin^2(u ea).
+// sin^2(th) = (1 - cos 2 th) / 2 with 2 th reduced to [-pi, pi] in turns (one MUFU.COS; absolute error ~1e-6 for the
+// |th| < 100 these activations see — the result is rounded to fp16 two steps later).
+DEVI float snake_beta(float u, float ea, float ib) {
+  float turns = u * ea * 0.318309886183790672f;
+  turns -= rintf(turns);
+  return fmaf(ib, fmaf(-0.5f, __cosf(turns * 6.283185307179586f), 0.5f), u);
+}
+
 // y = DownSample2(SnakeBeta(UpSample2(x)))   (Activation1d).  x = (x0 [+ x1 + x2]) * in_scale, [B, T, ld] of TIn;
 // ab: fp32 [2, ld]: row 0 = e^alpha, row 1 = 1 / (e^beta + 1e-9);  out: fp16 [B, T, ld].
 //   u[n] = 2 sum_j x[clamp(j)] f[n + 5 - 2 j]            (6 taps: j in [a-3, a+2] for n = 2a, [a-2, a+3] for n = 2a+1)
-//   s[n] = u + sin^2(u e^alpha) / (e^beta + 1e-9)
+//   s[n] = snake_beta(u[n])
 //   y[t] = sum_k s[clamp(2 t + k - 5, 0, 2T-1)] f[k]
-template <typename TIn>
+// A block stages AA_ROWS + 12 input rows x 64 channels in shared memory (coalesced, index-clamped = the replicate
+// padding of x); then one thread = one channel x AA_L consecutive outputs: the 2x-rate snake samples slide through a
+// 12-deep register window and every output is formed the moment its last sample exists — the 2x-rate signal never
+// touches shared or global memory.  Chunks in which the 2x-rate signal itself is replicate-padded (sequence ends) take
+// a clamped-index path.
+constexpr int AA_ROWS = AA_L * (AA_THREADS / AA_CH);   // 128 output rows per block
+
+template <typename TIn, int NIN>
 __global__ void __launch_bounds__(AA_THREADS)
 snake_aa_kernel(const TIn* __restrict__ x0, const TIn* __restrict__ x1, const TIn* __restrict__ x2, float in_scale,
                 const float* __restrict__ ab, __half* __restrict__ out, int T, int ld, AaFilter flt) {
-  __shared__ float xs[AA_XR][AA_CH];
-  __shared__ float ss[AA_SR][AA_CH];
+  __shared__ float xs[AA_ROWS + 12][AA_CH];    // xs[r] = x[clamp(tile0 - 6 + r)]
   const int c = threadIdx.x & (AA_CH - 1);
-  const int rlane = threadIdx.x / AA_CH;              // 0..3
-  constexpr int RL = AA_THREADS / AA_CH;
+  const int chunk = threadIdx.x / AA_CH;
   const int ch = blockIdx.y * AA_CH + c;
-  const int t0 = blockIdx.x * AA_TT;
+  const int tile0 = blockIdx.x * AA_ROWS;
   const long base = (long)blockIdx.z * T * ld + ch;
-  for (int r = rlane; r < AA_XR; r += RL) {
-    int j = t0 - 6 + r;
+  for (int r = chunk; r < AA_ROWS + 12; r += AA_THREADS / AA_CH) {
+    int j = tile0 - 6 + r;
     j = j < 0 ? 0 : (j > T - 1 ? T - 1 : j);
     const long off = base + (long)j * ld;
     float v = ld_as_float(x0 + off);
-    if (x1) v += ld_as_float(x1 + off);
-    if (x2) v += ld_as_float(x2 + off);
-    xs[r][c] = v * in_scale;
+    if constexpr (NIN == 3) v = (v + ld_as_float(x1 + off) + ld_as_float(x2 + off)) * in_scale;
+    xs[r][c] = v;
   }
   const float ea = ab[ch], ib = ab[ld + ch];
   __syncthreads();
-  for (int r = rlane; r < AA_SR; r += RL) {
-    int n = 2 * t0 - 5 + r;
-    n = n < 0 ? 0 : (n > 2 * T - 1 ? 2 * T - 1 : n);
-    const int a = n >> 1;
-    // rows of xs: index j - (t0 - 6)
-    float u = 0.f;
-    if ((n & 1) == 0) {
-      const int r0 = a - 3 - (t0 - 6);
+  const int t0 = tile0 + chunk * AA_L;
+  if (t0 >= T) return;
+  const int r0 = chunk * AA_L;                 // xs row of x[t0 - 6]
+  if (t0 >= 3 && t0 + AA_L + 2 <= T - 1) {     // every 2x-rate index 2 t0 - 5 .. 2 t0 + 2 L + 4 lies inside [0, 2T - 1]
+    // Iteration i (a = t0 - 3 + i, x[a - 3] = xs[r0 + i]) forms s[2a], then the output t = a - 3 from the 12 latest
+    // samples, then s[2a + 1].  Six iterations push 12 samples = one full turn of the window, so inside a group of
+    // six every window slot is a compile-time register (no shifting); the groups run in a rolled loop.  The first
+    // even sample (i = 0) and the last odd one are not needed — pushing them anyway is harmless (they fall out of /
+    // never enter a window that is read) and keeps the groups uniform.
+    float sw[12];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) u = fmaf(xs[r0 + i][c], flt.f[11 - 2 * i], u);   // j = a-3+i, tap = 2a+5-2j = 11-2i
-    } else {
-      const int r0 = a - 2 - (t0 - 6);
+    for (int i = 0; i < 12; ++i) sw[i] = 0.f;
+    static_assert((AA_L + 6) % 6 == 0, "AA_L + 6 must be a multiple of 6");
+#pragma unroll 1
+    for (int g = 0; g < (AA_L + 6) / 6; ++g) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) u = fmaf(xs[r0 + i][c], flt.f[10 - 2 * i], u);   // j = a-2+i, tap = 2a+6-2j = 10-2i
+      for (int ii = 0; ii < 6; ++ii) {
+        const int i = g * 6 + ii;
+        float xw[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) xw[q] = xs[r0 + i + q][c];
+        float u = 0.f;                          // s[2a]: j = a-3 .. a+2, taps 11, 9, .., 1
+#pragma unroll
+        for (int q = 0; q < 6; ++q) u = fmaf(xw[q], flt.f[11 - 2 * q], u);
+        sw[2 * ii] = snake_beta(2.0f * u, ea, ib);
+        if (g > 0) {                            // chronological order: slots 2ii+1 .. 11, then 0 .. 2ii
+          float y = 0.f;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) y = fmaf(sw[(2 * ii + 1 + k) % 12], flt.f[k], y);
+          out[base + (long)(t0 + i - 6) * ld] = __float2half_rn(y);
+        }
+        u = 0.f;                                // s[2a + 1]: j = a-2 .. a+3, taps 10, 8, .., 0
+#pragma unroll
+        for (int q = 0; q < 6; ++q) u = fmaf(xw[1 + q], flt.f[10 - 2 * q], u);
+        sw[2 * ii + 1] = snake_beta(2.0f * u, ea, ib);
+      }
     }
-    u *= 2.0f;
-    const float sn = sinf(u * ea);
-    ss[r][c] = fmaf(ib * sn, sn, u);
+    return;
   }
-  __syncthreads();
-  for (int r = rlane; r < AA_TT; r += RL) {
-    const int t = t0 + r;
-    if (t >= T) break;
+  // sequence ends: the 2x-rate index is clamped too, straight from the definition
+  const int t_end = min(T, t0 + AA_L);
+  for (int t = t0; t < t_end; ++t) {
     float y = 0.f;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) y = fmaf(ss[2 * r + k][c], flt.f[k], y);
+    for (int k = 0; k < 12; ++k) {
+      int n = 2 * t + k - 5;
+      n = n < 0 ? 0 : (n > 2 * T - 1 ? 2 * T - 1 : n);
+      const int a = n >> 1;
+      const int j0 = (n & 1) ? a - 2 : a - 3;  // first input row of this sample
+      const int tap0 = (n & 1) ? 10 : 11;
+      float u = 0.f;
+      for (int q = 0; q < 6; ++q) u = fmaf(xs[j0 + q - (tile0 - 6)][c], flt.f[tap0 - 2 * q], u);
+      y = fmaf(snake_beta(2.0f * u, ea, ib), flt.f[k], y);
+    }
     out[base + (long)t * ld] = __float2half_rn(y);
   }
 }
@@ -157,8 +195,11 @@ static int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64
 template <typename TIn>
 static int snake_aa(const TIn* x0, const TIn* x1, const TIn* x2, float scale, const float* ab, __half* out, int batch, int T,
                     int ld, const AaFilter& flt, cudaStream_t st) {
-  dim3 grid((T + AA_TT - 1) / AA_TT, ld / AA_CH, batch);
-  snake_aa_kernel<TIn><<<grid, AA_THREADS, 0, st>>>(x0, x1, x2, scale, ab, out, T, ld, flt);
+  dim3 grid((T + AA_ROWS - 1) / AA_ROWS, ld / AA_CH, batch);
+  if (x1 != nullptr)
+    snake_aa_kernel<TIn, 3><<<grid, AA_THREADS, 0, st>>>(x0, x1, x2, scale, ab, out, T, ld, flt);
+  else
+    snake_aa_kernel<TIn, 1><<<grid, AA_THREADS, 0, st>>>(x0, x1, x2, scale, ab, out, T, ld, flt);
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
 }

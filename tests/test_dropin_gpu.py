@@ -81,3 +81,37 @@ def test_streaming_yields_chunks(assets):
                                       progress=None, nfe_step=2, device="cuda", streaming=True, chunk_size=2048))
     assert all(sr_ == 24000 for _, sr_ in chunks) and all(len(c) <= 2048 for c, _ in chunks)
     assert sum(len(c) for c, _ in chunks) == (int(36000 // 256 / 20 * 30) - 1) * 256
+
+
+def test_tts_infer_with_the_bigvgan_branch(assets, tmp_path):
+    """`mel_spec_type: bigvgan` (configs/*.yaml:65 "vocos | bigvgan"): the Slaney-mel front-end for the reference audio
+    (modules.py:30-72), `load_vocoder("bigvgan", local dir)` (utils_infer.py:144-158) and `vocoder(mel)` (:550-551)."""
+    import json
+
+    import yaml
+
+    from lemas_tts.api import TTS
+
+    d, vocab = assets
+    cfg = yaml.safe_load((d / "tiny.yaml").read_text())
+    cfg["model"]["mel_spec"]["mel_spec_type"] = "bigvgan"
+    (tmp_path / "tiny_bigvgan.yaml").write_text(yaml.safe_dump(cfg))
+    import dataclasses
+
+    arch = dataclasses.replace(syn.FULL_BIGVGAN, upsample_initial_channel=128)   # 256x up-sampling, 64 ... 2 channels
+    voc = tmp_path / "bigvgan_v2_24khz_100band_256x"
+    voc.mkdir()
+    (voc / "config.json").write_text(json.dumps(arch.to_config()))
+    torch.save({"generator": syn.make_bigvgan_state_dict(arch, seed=5)}, voc / "bigvgan_generator.pt")
+    tts = TTS(model=str(tmp_path / "tiny_bigvgan.yaml"), ckpt_file=str(d / "model.safetensors"),
+              vocab_file=str(d / "vocab.txt"), use_ema=True, vocoder_local_path=str(voc), device="cuda", frontend=None)
+    assert tts.mel_spec_type == "bigvgan"
+    ref_text = vocab[1:21]
+    gen_text = [vocab[5:35], vocab[10:26]]
+    wav, sr, spec = tts.infer(str(d / "ref.wav"), ref_text, gen_text, nfe_step=4, cfg_strength=2, sway_sampling_coef=5,
+                              seed=123, progress=None)
+    assert sr == 24000 and wav.ndim == 1 and np.isfinite(wav).all() and np.abs(wav).max() > 0
+    ref_frames = 36000 // 256
+    exp_frames = [int(ref_frames / 20 * 30), int(ref_frames / 20 * 16)]
+    assert spec.shape == (100, sum(exp_frames))
+    assert len(wav) == sum(f * 256 for f in exp_frames) - int(0.15 * 24000)       # BigVGAN: 256 samples per frame

@@ -183,6 +183,26 @@ def test_dense_conv7_bias_f32():
     _close(out.view(B, T, Cout), ref.transpose(1, 2), what="dense conv")
 
 
+@pytest.mark.parametrize("k,dil,C,bn", [(3, 5, 64, 64), (7, 3, 192, 64), (11, 5, 128, 128), (11, 1, 256, 256)])
+def test_dilated_conv_gate_resid(k, dil, C, bn):
+    """BigVGAN AMPBlock1 convolutions (Conv1d(C, C, k, dilation d, padding d (k-1)/2)) as tap GEMMs with
+    lemas_gemm_desc.tap_dilation; residual epilogue with gate = NULL (= 1), two sequences (zero padding at both ends)."""
+    from lemas_tts import ops, _native as nv
+
+    B, T = 2, 333
+    x = _rand((B, T, C), 40 + k, dtype=torch.float16)
+    wt = _rand((C, C, k), 41 + k, 1 / math.sqrt(k * C))
+    bias = _rand((C,), 42 + k)
+    res = _rand((B * T, C), 43 + k)
+    w_tap = wt.permute(2, 0, 1).contiguous().to(torch.float16).view(k * C, C)
+    out = torch.zeros(B * T, C, device="cuda")
+    ops.gemm(x, w_tap, epilogue=nv.EPI_GATE_RESID_F32, n=C, bias=bias, block_n=bn, out32=out, resid=res, taps=k,
+             tap_pad=(k - 1) // 2, tap_dilation=dil, w_tap_stride=C, k_per_tap=C, seq_len=T)
+    torch.cuda.synchronize()
+    ref = F.conv1d(x.float().transpose(1, 2), wt.to(torch.float16).float(), bias, dilation=dil, padding=dil * (k - 1) // 2)
+    _close(out.view(B, T, C), ref.transpose(1, 2) + res.view(B, T, C), what=f"dilated conv k={k} d={dil}")
+
+
 def test_mish_resid_f32():
     from lemas_tts import ops, _native as nv
 
