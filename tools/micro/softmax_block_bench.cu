@@ -14,6 +14,10 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) { 
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack(float a, float b) { uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r; }
+__device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ void unpack_h2(uint32_t v, float& lo, float& hi) {
+  asm("{ .reg .f16 a, b; mov.b32 {a, b}, %2; cvt.f32.f16 %0, a; cvt.f32.f16 %1, b; }" : "=f"(lo), "=f"(hi) : "r"(v));
+}
 __device__ __forceinline__ float fmax3f(float a, float b, float c) { float y; asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c)); return y; }
 
 template <int VAR, int DEPTH>
@@ -36,6 +40,24 @@ __global__ void __launch_bounds__(512, 1) k(const float* in, uint32_t* out, long
       for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], s[i], s[32 + i]);
       const float mx = fmaxf(fmax3f(m4[0], m4[1], m4[2]), m4[3]);
       if (__any_sync(0xffffffffu, (mx - mc) * c > 8.f)) mc = mx;
+    }
+    if (VAR == 9 || VAR == 10) {  // max pass: FMNMX3, 4 chains
+      float m4[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmax3f(m4[i & 3], s[i], s[32 + i]);
+      const float mx = fmaxf(fmax3f(m4[0], m4[1], m4[2]), m4[3]);
+      if (__any_sync(0xffffffffu, (mx - mc) * c > 8.f)) mc = mx;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {   // (s c - m c) in fp32, packed to f16x2, ONE MUFU per key pair; P is already packed
+        float x0, x1;
+        split(ffma2(f32x2(s[2 * i], s[2 * i + 1]), c2, nmc2), x0, x1);
+        pk[i] = ex2h2(pack(x0, x1));
+        if (VAR == 10) {               // fp32 row sum from the packed halves (instead of a ones-column in V)
+          float e0, e1;
+          unpack_h2(pk[i], e0, e1);
+          rs2[i & 3] = fadd2(rs2[i & 3], f32x2(e0, e1));
+        }
+      }
     }
     if (VAR == 5 || VAR == 7) {  // max pass: FMNMX3, 4 chains (the kernels' current form)
       float m4[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
@@ -173,6 +195,8 @@ int main() {
   run<7, 1>("FMNMX3 max + 1/4 poly (v6 body)", in, out, clk);
   run<8, 1>("FMNMX 8-chain max + 1/4 poly", in, out, clk);
   run<8, 2>("FMNMX 8-chain max + 2/4 poly", in, out, clk);
+  run<9, 0>("FMNMX3 max + ex2.f16x2, no row sum", in, out, clk);
+  run<10, 0>("FMNMX3 max + ex2.f16x2 + fp32 sum (unpack)", in, out, clk);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return 0;
