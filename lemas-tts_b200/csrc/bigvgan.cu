@@ -76,6 +76,11 @@ snake_aa_kernel(const TIn* __restrict__ x0, const TIn* __restrict__ x1, const TI
   __syncthreads();
   const int t0 = tile0 + chunk * AA_L;
   if (t0 >= T) return;
+  if (ea == 0.f) {   // padded channel (e^alpha > 0 for every real one): snake(0) = 0, nothing to compute
+    const int t_end = min(T, t0 + AA_L);
+    for (int t = t0; t < t_end; ++t) out[base + (long)t * ld] = __float2half_rn(0.f);
+    return;
+  }
   const int r0 = chunk * AA_L;                 // xs row of x[t0 - 6]
   if (t0 >= 3 && t0 + AA_L + 2 <= T - 1) {     // every 2x-rate index 2 t0 - 5 .. 2 t0 + 2 L + 4 lies inside [0, 2T - 1]
     // Iteration i (a = t0 - 3 + i, x[a - 3] = xs[r0 + i]) forms s[2a], then the output t = a - 3 from the 12 latest
