@@ -452,7 +452,8 @@ int attention_variant() {
 
 // LEMAS_ATT_VARIANT / lemas_debug_attention_variant: 0 = v3 (this file, production); 7 / 8 / 9 = v7 (attention7.cu,
 // experimental: persistent CTA, double-buffered scores, four key parts) with 0, 1/4, 3/8 of the exp2 on the FMA pipe;
-// 18-21 = v7 timing ablations (wrong results).  LEMAS_A7_DEPHASE (clocks) sets v7's start-up stagger.
+// 18-21 = v7 timing ablations (wrong results); 30 = v8 (attention8.cu, experimental: v3's pipeline in a persistent CTA).
+// LEMAS_A7_DEPHASE (clocks) sets v7's start-up stagger.
 extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,
                                    void* out16, int32_t batch, int32_t seq, int32_t heads, void* stream) {
   LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
@@ -495,5 +496,6 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   p.dephase_tile = dephase_tile;
   p.n_pairs = (seq + 127) / 128;   // 128-query tiles per (batch, head)
   p.n_items = p.n_pairs * heads * batch;
+  if (variant == 30) return attention_v8_launch(tmQK, tmVT, p, stream);   // v8: v3's pipeline in a persistent CTA
   return attention_v7_launch(tmQK, tmVT, p, variant - 7, stream);
 }

@@ -47,6 +47,9 @@ def main():
     if variant != "sdpa":
         lib.lemas_debug_attention_variant(int(variant))
     for name in shapes:
+        if name not in SHAPES and "x" in name:      # ad-hoc uniform shape "B2xSEQ", e.g. 2x4736
+            b2, sq = name.split("x")
+            SHAPES[name] = (int(b2), int(sq), None)
         B2, seq, lens = SHAPES[name]
         g = torch.Generator(device="cuda").manual_seed(0)
         npad = (seq + 63) // 64 * 64
