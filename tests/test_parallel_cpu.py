@@ -114,3 +114,30 @@ def test_synthesize_sharded_two_ranks_gathers_in_list_order(tmp_path):
         assert len(res[key]) == len(utts)
         for i in range(len(utts)):
             assert torch.equal(res[key][i], want[i]), (key, i)
+
+
+def test_shard_utterances_properties():
+    """Property test (hypothesis): for any list of lengths and world size the shards are a partition of the indices, in
+    ascending order inside a rank, identical on every call (ranks compute them independently), and balanced the way
+    longest-first greedy guarantees: no rank exceeds the lightest one by more than one utterance's cost."""
+    from hypothesis import given, settings, strategies as st
+
+    from lemas_tts.parallel import shard_utterances
+
+    def cost(n):
+        return n * (378_888_192 + 90_112 * n)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=4096), min_size=0, max_size=70), st.integers(1, 8))
+    def check(lengths, world):
+        shards = shard_utterances(lengths, world)
+        assert len(shards) == world
+        flat = [i for s in shards for i in s]
+        assert sorted(flat) == list(range(len(lengths)))
+        assert all(s == sorted(s) for s in shards)
+        assert shards == shard_utterances(list(lengths), world)
+        loads = [sum(cost(lengths[i]) for i in s) for s in shards]
+        if lengths:
+            assert max(loads) - min(loads) <= cost(max(lengths))
+
+    check()
