@@ -171,6 +171,11 @@ int lemas_istft_1024(const float* head, int32_t ld_head, float* frames_ws, float
  * filter; mel: fp32 [batch, n_mels, nw/256 + 1]. */
 int lemas_mel_spectrogram_1024(const float* wav, int32_t batch, int32_t nw, int32_t wav_ld, const float* fb,
                                const int32_t* fb_range, int32_t n_mels, float* mel, void* stream);
+/* Same kernel for the `mel_spec_type: bigvgan` front-end (get_bigvgan_mel_spectrogram, modules.py:30-72): reflect padding of
+ * (1024 - 256) / 2 samples, no centering, sqrt(re^2 + im^2 + 1e-9); fb = Slaney mel filterbank with Slaney norm
+ * (librosa.filters.mel) in the [513, n_mels] layout; nw > 384; mel: fp32 [batch, n_mels, (nw - 256) / 256 + 1]. */
+int lemas_mel_spectrogram_bigvgan_1024(const float* wav, int32_t batch, int32_t nw, int32_t wav_ld, const float* fb,
+                                       const int32_t* fb_range, int32_t n_mels, float* mel, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Engine-level entry points: the whole sampler / vocoder as a sequence of the launches above, driven from C++.

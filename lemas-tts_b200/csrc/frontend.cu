@@ -20,7 +20,7 @@ constexpr int MEL_BINS = MEL_NFFT / 2 + 1;
 
 __global__ void __launch_bounds__(256)
 mel_frames_kernel(const float* __restrict__ wav, int nw, int wav_ld, const float* __restrict__ fb,
-                  const int* __restrict__ fb_range, int n_mels, int t_len, float* __restrict__ mel) {
+                  const int* __restrict__ fb_range, int n_mels, int t_len, float* __restrict__ mel, int pad, float mag_eps) {
   __shared__ float2 buf[MEL_NFFT];
   __shared__ float2 tw[MEL_NFFT / 2];
   __shared__ float mag[MEL_BINS];
@@ -33,7 +33,8 @@ mel_frames_kernel(const float* __restrict__ wav, int nw, int wav_ld, const float
     tw[k] = make_float2(c, s);
   }
   for (int n = threadIdx.x; n < MEL_NFFT; n += blockDim.x) {
-    int i = frame * MEL_HOP + n - MEL_NFFT / 2;          // center=True: frame t covers [t*hop - 512, t*hop + 512)
+    int i = frame * MEL_HOP + n - pad;                   // pad 512: center=True, frame t covers [t*hop - 512, t*hop + 512);
+                                                         // pad 384: bigvgan's explicit (n_fft - hop) / 2 padding, center=False
     if (i < 0) i = -i;                                   // pad_mode="reflect" (no edge repeat)
     if (i >= nw) i = 2 * (nw - 1) - i;
     const float win = 0.5f - 0.5f * cospif((float)n * (2.0f / MEL_NFFT));   // periodic hann
@@ -55,7 +56,7 @@ mel_frames_kernel(const float* __restrict__ wav, int nw, int wav_ld, const float
     }
     __syncthreads();
   }
-  for (int k = threadIdx.x; k < MEL_BINS; k += blockDim.x) mag[k] = sqrtf(buf[k].x * buf[k].x + buf[k].y * buf[k].y);
+  for (int k = threadIdx.x; k < MEL_BINS; k += blockDim.x) mag[k] = sqrtf(buf[k].x * buf[k].x + buf[k].y * buf[k].y + mag_eps);
   __syncthreads();
   for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
     const int lo = fb_range[2 * m], hi = fb_range[2 * m + 1];
@@ -75,7 +76,27 @@ extern "C" int lemas_mel_spectrogram_1024(const float* wav, int32_t batch, int32
   LEMAS_REQUIRE(batch >= 1 && n_mels >= 1 && wav_ld >= nw, "lemas_mel_spectrogram_1024: bad shape");
   LEMAS_REQUIRE(nw > MEL_NFFT / 2, "lemas_mel_spectrogram_1024: reflect padding needs more than 512 samples");
   const int t_len = nw / MEL_HOP + 1;
-  mel_frames_kernel<<<batch * t_len, 256, 0, (cudaStream_t)stream>>>(wav, nw, wav_ld, fb, fb_range, n_mels, t_len, mel);
+  mel_frames_kernel<<<batch * t_len, 256, 0, (cudaStream_t)stream>>>(wav, nw, wav_ld, fb, fb_range, n_mels, t_len, mel,
+                                                                     MEL_NFFT / 2, 0.f);
+  LEMAS_CUDA_OK(cudaGetLastError());
+  LEMAS_LAUNCHED(1);
+  return LEMAS_OK;
+}
+
+// The `mel_spec_type: bigvgan` front-end (get_bigvgan_mel_spectrogram, modules.py:30-72): reflect padding of
+// (n_fft - hop) / 2 = 384 samples, STFT without centering, sqrt(re^2 + im^2 + 1e-9), filterbank (Slaney mel, Slaney norm:
+// what librosa.filters.mel returns, in the same [513, n_mels] layout as above), log(clamp 1e-5).
+// mel: fp32 [batch, n_mels, (nw - 256) / 256 + 1].
+extern "C" int lemas_mel_spectrogram_bigvgan_1024(const float* wav, int32_t batch, int32_t nw, int32_t wav_ld,
+                                                  const float* fb, const int32_t* fb_range, int32_t n_mels, float* mel,
+                                                  void* stream) {
+  LEMAS_REQUIRE(wav && fb && fb_range && mel, "lemas_mel_spectrogram_bigvgan_1024: null pointer");
+  LEMAS_REQUIRE(batch >= 1 && n_mels >= 1 && wav_ld >= nw, "lemas_mel_spectrogram_bigvgan_1024: bad shape");
+  constexpr int pad = (MEL_NFFT - MEL_HOP) / 2;
+  LEMAS_REQUIRE(nw > pad, "lemas_mel_spectrogram_bigvgan_1024: reflect padding needs more than 384 samples");
+  const int t_len = (nw + 2 * pad - MEL_NFFT) / MEL_HOP + 1;
+  mel_frames_kernel<<<batch * t_len, 256, 0, (cudaStream_t)stream>>>(wav, nw, wav_ld, fb, fb_range, n_mels, t_len, mel, pad,
+                                                                     1e-9f);
   LEMAS_CUDA_OK(cudaGetLastError());
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;

@@ -150,6 +150,7 @@ SIGNATURES = {
     "lemas_dwconv7_ln": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "lemas_istft_1024": (C.c_int, [vp, i32, vp, vp, i32, i32, vp]),
     "lemas_mel_spectrogram_1024": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "lemas_mel_spectrogram_bigvgan_1024": (C.c_int, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
     "lemas_audio_prep_workspace_bytes": (i64, [i64]),
     "lemas_audio_prep": (C.c_int, [vp, i32, i64, i64, f32, vp, vp, vp, i64, vp]),
     "lemas_audio_unscale": (C.c_int, [vp, i64, vp, vp]),

@@ -68,6 +68,10 @@ def get_bigvgan_mel_spectrogram(waveform, n_fft=1024, n_mel_channels=100, target
         _MEL_CACHE[key] = (slaney_mel_filterbank(target_sample_rate, n_fft, n_mel_channels, fmin, fmax).to(waveform.device),
                            torch.hann_window(win_length, device=waveform.device))
     mel_basis, window = _MEL_CACHE[key]
+    if (waveform.is_cuda and (n_fft, hop_length, win_length) == (1024, 256, 1024) and not center
+            and waveform.shape[-1] > 384):
+        from lemas_tts import ops
+        return ops.mel_spectrogram_bigvgan_1024(waveform.float().contiguous(), mel_basis)
     pad = (n_fft - hop_length) // 2
     x = F.pad(waveform.float().unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
     spec = torch.stft(x, n_fft, hop_length=hop_length, win_length=win_length, window=window, center=center,

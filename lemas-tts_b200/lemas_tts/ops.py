@@ -179,6 +179,30 @@ def mel_spectrogram_1024(wav: torch.Tensor, n_mels: int = 100, sample_rate: int 
 
 
 @nv.on_device
+def mel_spectrogram_bigvgan_1024(wav: torch.Tensor, fb_mel_by_freq: torch.Tensor) -> torch.Tensor:
+    """wav: fp32 [b, nw] on the GPU; fb_mel_by_freq: Slaney filterbank [n_mels, 513] -> log-mel fp32
+    [b, n_mels, (nw - 256) // 256 + 1]   (get_bigvgan_mel_spectrogram, modules.py:30-72; csrc/frontend.cu)."""
+    nv.require_device()
+    _chk(wav, f32, "wav")
+    assert wav.dim() == 2
+    n_mels = fb_mel_by_freq.shape[0]
+    key = ("bigvgan", wav.device, n_mels, fb_mel_by_freq.data_ptr())
+    if key not in _MEL_FB:
+        fb = fb_mel_by_freq.detach().float().t().contiguous().cpu()          # [513, n_mels]
+        nz = fb > 0
+        first = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        last = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(n_mels, dtype=torch.long))
+        rng = torch.stack((first, last), dim=1).to(torch.int32).contiguous()
+        _MEL_FB[key] = (fb.to(wav.device), rng.to(wav.device))
+    fb, rng = _MEL_FB[key]
+    b, nw = wav.shape
+    mel = torch.empty(b, n_mels, (nw - 256) // 256 + 1, device=wav.device, dtype=f32)
+    nv.check(nv.load().lemas_mel_spectrogram_bigvgan_1024(nv.ptr(wav), b, nw, wav.stride(0), nv.ptr(fb), nv.ptr(rng), n_mels,
+                                                          nv.ptr(mel), nv.stream()))
+    return mel
+
+
+@nv.on_device
 def istft_1024(head: torch.Tensor, batch: int, t: int) -> torch.Tensor:
     """head: [batch*t, ld>=1026] fp32 rows (log-mag | phase) -> wav [batch, (t-1)*256]."""
     nv.require_device()

@@ -60,3 +60,26 @@ def test_mel_strided_batch_rows():
     nv.check(nv.load().lemas_mel_spectrogram_1024(wav.data_ptr(), 2, 7000, wav.stride(0), nv.ptr(fb_d),
                                                   nv.ptr(rng_d), 100, nv.ptr(mel), nv.stream()))
     assert (mel.cpu() - want).abs().max().item() < TOL
+
+
+def test_bigvgan_mel_frontend_matches_reference_golden():
+    """`mel_spec_type: bigvgan` (get_bigvgan_mel_spectrogram, /root/reference/lemas_tts/model/modules.py:30-72) through
+    the native STFT + mel kernel (lemas_mel_spectrogram_bigvgan_1024): golden minted by the VERBATIM reference function
+    (oracle/gen_golden_bigvgan.py).  log-mel, fp32: max-abs 2e-4 (same bar as the vocos front-end test)."""
+    from lemas_tts import _native as nv
+    from lemas_tts.model.modules import MelSpec
+
+    want = torch.load(gc.GOLDEN / "bigvgan_mel.pt", weights_only=True)["mel"]
+    wav = syn.synthetic_ref_audio(2, 24000 + 77, seed=21)
+    before = nv.load().lemas_launch_count()
+    got = MelSpec(mel_spec_type="bigvgan")(wav.cuda())
+    assert nv.load().lemas_launch_count() == before + 1, "the native kernel did not run"
+    assert got.shape == want.shape
+    err = (got.cpu() - want).abs().max().item()
+    print(f"bigvgan mel front-end: max abs err {err:.2e}")
+    assert err < 2e-4
+    # strided rows (a batch sliced out of a wider buffer) and the torch path on the CPU agree as well
+    wide = torch.zeros(2, 30000, device="cuda")
+    wide[:, : wav.shape[1]] = wav.cuda()
+    again = MelSpec(mel_spec_type="bigvgan")(wide[:, : wav.shape[1]])
+    assert torch.equal(again, got)
