@@ -274,7 +274,8 @@ enum lemas_prof_kind {
   LEMAS_PROF_GEMM_FF2 = 8,
   LEMAS_PROF_PROJ_OUT = 9,
   LEMAS_PROF_CFG_EULER = 10,
-  LEMAS_PROF_KINDS = 11
+  LEMAS_PROF_TARE = 11,     /* an EMPTY event pair per ODE step: the cost of the measurement itself      */
+  LEMAS_PROF_KINDS = 12
 };
 int lemas_engine_profile(lemas_engine* e, int32_t enable);
 int lemas_engine_profile_read(lemas_engine* e, double* ms, int64_t* launches, void* stream);

@@ -117,7 +117,8 @@ struct lemas_engine {
 static const char* const kProfNames[LEMAS_PROF_KINDS] = {
     "K1/K12 preloop (time MLP, AdaLN table, invariant input projection)", "K9 in_proj", "K10 conv_pos + Mish",
     "K2 LN + modulate", "K3/K5 QKV GEMM + RoPE", "K6 attention", "K7 to_out GEMM + gate + residual",
-    "K8 FF1 GEMM + GELU", "K8 FF2 GEMM + gate + residual", "K13 proj_out", "K13-K15 CFG + clamp + Euler"};
+    "K8 FF1 GEMM + GELU", "K8 FF2 GEMM + gate + residual", "K13 proj_out", "K13-K15 CFG + clamp + Euler",
+    "empty event pair (measurement tare)"};
 
 struct ProfScope {
   lemas_engine* e; cudaStream_t st; ProfRecord r; bool on; bool range; unsigned ext = 0;
@@ -400,6 +401,7 @@ static int ode_step(lemas_engine* e, const DitBuffers& b, const lemas_sample_arg
   int* row_limit = (kv2 != nullptr && (a->flags & LEMAS_SAMPLE_SKIP_PADDED_ROWS)) ? b.row_limit : nullptr;
   const int rows = a->batch * a->seq;
   const int64_t mod_w = (int64_t)c.depth * 6 * c.dim + 2 * c.dim;
+  { PROF(LEMAS_PROF_TARE); }   // nothing between the two records: what an event pair itself adds to every bracket
   {
     PROF(LEMAS_PROF_CFG_EULER);
     LEMAS_TRY(step_begin_launch(b.mod, mod_w, b.mod_cur, b.t_dev, b.step_ctr, b.state,

@@ -22,7 +22,7 @@ EPI_BIAS_F32, EPI_ADD_F32_F16, EPI_MISH_F16, EPI_MISH_RESID_F32 = 5, 6, 7, 8
 SAMPLE_SKIP_PADDED_ROWS = 1
 SAMPLE_FOLD_LAYERNORM = 2
 PROF_KINDS = ["preloop", "in_proj", "conv_pos", "ln_mod", "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
-              "proj_out", "cfg_euler"]
+              "proj_out", "cfg_euler", "tare"]
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
