@@ -110,6 +110,17 @@ DEVI void epilogue_chunk(const GemmParams& p, float (&v)[32], long grow, int col
     const float4* r = reinterpret_cast<const float4*>(p.resid + grow * p.ldr + col0);
     float4* o = reinterpret_cast<float4*>(p.out32 + grow * p.ld32 + col0);
     const float4* g = p.gate ? reinterpret_cast<const float4*>(p.gate + (long)b * p.gate_bstride + col0) : nullptr;
+    if (p.red_add == 2) {   // in place: x += gate (acc + bias) as 16-byte reductions in the L2 (see gemm2.cu)
+      if (!dead) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 gg = g ? __ldg(g + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(gg.x * v[4 * i]),
+                       "f"(gg.y * v[4 * i + 1]), "f"(gg.z * v[4 * i + 2]), "f"(gg.w * v[4 * i + 3]) : "memory");
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 rr = r[i];
@@ -351,6 +362,11 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
   p.resid = d.resid; p.ldr = d.ldr;
   p.gate = d.gate; p.gate_bstride = d.gate_bstride;
   p.row_valid = d.row_valid; p.seq_len = d.seq_len; p.row_limit = d.row_limit;
+  {
+    static const int red = [] { const char* e = getenv("LEMAS_G2_RED"); return e ? atoi(e) : 1; }();   // 0: load + add + store
+    p.red_add = (red != 0 && d.epilogue == LEMAS_EPI_GATE_RESID_F32 && d.resid == d.out32 && d.ldr == d.ld32 &&
+                 d.ln_out16 == nullptr) ? 1 : 0;
+  }
   p.ln_scale = d.ln_scale; p.ln_out16 = static_cast<__half*>(d.ln_out16); p.ln_ld16 = d.ln_ld16; p.ln_stats = d.ln_stats;
   p.ln_stats_in = d.ln_stats_in; p.ln_parts = d.ln_parts; p.ln_uv = d.ln_uv; p.ln_step = d.ln_step;
   p.ln_inv_k = d.ln_k > 0 ? 1.0f / (float)d.ln_k : 0.f;
@@ -375,6 +391,11 @@ int gemm_launch(const lemas_gemm_desc& d, cudaStream_t stream) {
                   "lemas_gemm_f16: QKV epilogue needs rope table, vt buffer and n == 3*inner");
 
   if (pair_enabled() && gemm2_eligible(d)) return gemm2_launch(d, p, stream);
+  {
+    static const int red1 = [] { const char* e = getenv("LEMAS_G1_RED"); return e ? atoi(e) : 1; }();   // 0: load + add + store
+    p.red_add = (red1 != 0 && d.epilogue == LEMAS_EPI_GATE_RESID_F32 && d.resid == d.out32 && d.ldr == d.ld32 &&
+                 d.n % 32 == 0) ? 2 : 0;
+  }
   LEMAS_REQUIRE(d.ln_out16 == nullptr && d.ln_stats_in == nullptr,
                 "lemas_gemm_f16: the folded LayerNorm needs the CTA-pair kernel (block_n 256, n % 256 == 0)");
 

@@ -15,6 +15,8 @@ struct GemmParams {
   const float* gate; int gate_bstride;
   const int* row_valid;
   const int* row_limit;   // gemm2 only: tiles starting at or beyond row_limit[batch item] are skipped
+  int red_add;            // gemm2 gated-residual epilogue, in place (resid == out32): x += gate * (acc + bias) as one
+                          // vector reduction in L2 (red.global.add.v4.f32) instead of load + add + store
   // LayerNorm folded into the surrounding GEMMs (gemm2 only; see lemas_gemm_desc)
   const float* ln_scale; __half* ln_out16; int ln_ld16; float* ln_stats;
   const float* ln_stats_in; int ln_parts; const float* ln_uv; const int* ln_step; float ln_inv_k;
