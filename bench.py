@@ -610,7 +610,9 @@ def run_b200(args):
                 "h2d_bytes_per_step": world * (cond_h.numel() * cond_h.element_size() + text_h.numel() * 8),
                 "d2h_bytes_per_step": world * wav_h.numel() * 4},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "attention_kernel (tcgen05, csrc/attention.cu)",
+        "roofline": {"bound": "tensor",
+                     "kernel": ("attention9_kernel (tcgen05, csrc/attention9.cu: short / ragged sequences)"
+                                if (wl.name == "C3" or N <= 1024) else "attention_kernel (tcgen05, csrc/attention.cu)"),
                      "achieved": att_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": att_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["source"],
                      "flops_per_launch": att_flops, "launch_ms": att_ms / att_n if att_n else None,

@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "build"
 LIB = HERE / "lib" / "liblemas_b200.so"
-SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention7.cu", "attention8.cu", "elementwise.cu", "engine.cu", "text.cu", "frontend.cu", "prosody.cu", "audio.cu", "bigvgan.cu"]
+SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention7.cu", "attention8.cu", "attention9.cu", "elementwise.cu", "engine.cu", "text.cu", "frontend.cu", "prosody.cu", "audio.cu", "bigvgan.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC"]

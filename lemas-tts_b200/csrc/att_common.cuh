@@ -17,6 +17,8 @@ struct AttnParams {
   int n_pairs, n_items;   // v7 only: 128-query tiles per (batch, head); work items = n_pairs * heads * batch
 };
 
+int attention_v9_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const AttnParams& p, int batch,
+                        void* stream);
 int attention_v8_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, void* stream);
 int attention_v7_launch(const CUtensorMap& tmQK, const CUtensorMap& tmVT, const AttnParams& p, int poly, void* stream);
 int attention_v3_launch(const void* qk, int32_t ld_qk, const void* vt, int32_t vt_ld, const int32_t* kv_len,

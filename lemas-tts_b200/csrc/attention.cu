@@ -437,7 +437,9 @@ extern "C" void lemas_debug_attention_trace(void* buf) { g_att_trace = static_ca
 extern "C" void lemas_debug_attention_variant(int v) { g_att_variant = v; }
 
 namespace {
-constexpr int kDefaultVariant = 0;   // v3 is the fastest measured kernel (C2: 59 us; v5 63, v6 / v7 71 us)
+constexpr int kAutoVariant = 100;    // choose between v3 and v9 by shape (see lemas_attention_f16)
+constexpr int kDefaultVariant = kAutoVariant;   // v3 is the fastest kernel on long sequences (C2: 59 us; v5 63, v6 / v7 71,
+                                                // v8 63 us), v9 on short and ragged ones
 int attention_variant() {
   if (g_att_variant >= 0) return g_att_variant;
   static int env = -2;
@@ -459,7 +461,12 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   LEMAS_REQUIRE(qk && vt && out16, "lemas_attention_f16: null pointer");
   LEMAS_REQUIRE(ld_qk % 8 == 0 && vt_ld % 8 == 0 && vt_ld >= seq, "lemas_attention_f16: ld_qk/vt_ld must be multiples of 8");
   LEMAS_REQUIRE(batch >= 1 && seq >= 1 && heads >= 1, "lemas_attention_f16: bad shape");
-  const int variant = attention_variant();
+  int variant = attention_variant();
+  // Default choice by shape (LEMAS_ATT_VARIANT = 0 forces v3, 40 forces v9): short sequences and ragged batches go to v9
+  // (attention9.cu: one 64-key pipeline per CTA, four CTAs per SM — twice the blocks per CTA, no merge: C4's 768 keys
+  // 229 vs 238 us, the ragged C3 mix 227 vs 246 us); long uniform sequences stay on v3 (C2 59.5 vs 60.2 us, C5 88 vs 100:
+  // v9's 592 CTA slots quantise 704 tiles into two waves).  profiles/r02ah_attention_v9.log
+  if (variant == kAutoVariant) variant = (kv_len != nullptr || seq <= 1024) ? 40 : 0;
   if (variant < 7)
     return attention_v3_launch(qk, ld_qk, vt, vt_ld, kv_len, out16, batch, seq, heads, g_att_trace, stream);
   const int inner = heads * 64;
@@ -496,6 +503,7 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   p.dephase_tile = dephase_tile;
   p.n_pairs = (seq + 127) / 128;   // 128-query tiles per (batch, head)
   p.n_items = p.n_pairs * heads * batch;
+  if (variant == 40) return attention_v9_launch(qk, ld_qk, vt, vt_ld, p, batch, stream);   // v9: one 64-key pipeline per CTA
   if (variant == 30) return attention_v8_launch(tmQK, tmVT, p, stream);   // v8: v3's pipeline in a persistent CTA
   return attention_v7_launch(tmQK, tmVT, p, variant - 7, stream);
 }
