@@ -462,11 +462,16 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   LEMAS_REQUIRE(ld_qk % 8 == 0 && vt_ld % 8 == 0 && vt_ld >= seq, "lemas_attention_f16: ld_qk/vt_ld must be multiples of 8");
   LEMAS_REQUIRE(batch >= 1 && seq >= 1 && heads >= 1, "lemas_attention_f16: bad shape");
   int variant = attention_variant();
-  // Default choice by shape (LEMAS_ATT_VARIANT = 0 forces v3, 40 forces v9): short sequences and ragged batches go to v9
+  // Default choice by shape (LEMAS_ATT_VARIANT = 0 forces v3, 40 forces v9): BATCHES of short or ragged sequences go to v9
   // (attention9.cu: one 64-key pipeline per CTA, four CTAs per SM — twice the blocks per CTA, no merge: C4's 768 keys
   // 229 vs 238 us, the ragged C3 mix 227 vs 246 us); long uniform sequences stay on v3 (C2 59.5 vs 60.2 us, C5 88 vs 100:
   // v9's 592 CTA slots quantise 704 tiles into two waves).  profiles/r02ah_attention_v9.log
-  if (variant == kAutoVariant) variant = (kv_len != nullptr || seq <= 1024) ? 40 : 0;
+  // v9 needs enough tiles to fill its 4 x 148 CTA slots about twice: with few tiles (one short utterance: 2 x 1024 keys,
+  // 256 tiles) v3's two pipelines per tile finish in 16 us where v9's single one needs 28.
+  if (variant == kAutoVariant) {
+    const long tiles = (long)((seq + 127) / 128) * heads * batch;
+    variant = ((kv_len != nullptr || seq <= 1024) && tiles >= 8L * sm_count()) ? 40 : 0;
+  }
   if (variant < 7)
     return attention_v3_launch(qk, ld_qk, vt, vt_ld, kv_len, out16, batch, seq, heads, g_att_trace, stream);
   const int inner = heads * 64;
