@@ -55,6 +55,9 @@ def parse():
                     help="C3 (ragged batch): also compute the padded rows that cannot reach a valid row (reference-"
                          "identical padding; default: skip them, lemas_sample_args.flags)")
     ap.add_argument("--no-c4", action="store_true", help="skip the sharded C4 block (256 utterances over the ranks)")
+    ap.add_argument("--vocoder", default="vocos", choices=["vocos", "bigvgan"],
+                    help="vocos (both shipped configs) or the BigVGAN-v2 generator of the `mel_spec_type: bigvgan` branch "
+                         "(112 M parameters, seeded weights)")
     ap.add_argument("--latency-split", action="store_true",
                     help="--gpus 2 only: add a `latency_split` block — ONE utterance of the workload with the conditional "
                          "and unconditional forwards on the two GPUs (lemas_tts.parallel.CfgSplit) against one GPU")
@@ -393,9 +396,22 @@ def run_b200(args):
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
     model.skip_padded_rows = wl.name == "C3" and not args.all_rows
-    voc = Vocos()
-    voc.load_state_dict(vsd, strict=True)
-    voc = voc.to(dev).eval()
+    if args.vocoder == "bigvgan":   # every rank builds the same seeded generator (no broadcast needed for the bench)
+        from lemas_tts.bigvgan import BigVGAN
+
+        big = BigVGAN()
+        big.load_state_dict(syn.make_bigvgan_state_dict(syn.FULL_BIGVGAN, seed=17), strict=True)
+        big = big.to(dev).eval()
+
+        class _AsDecode:   # same call shape as Vocos.decode for the code below: [B, 100, T] -> [B, samples]
+            def decode(self, mel):
+                return big(mel)[:, 0, : (mel.shape[-1] - 1) * HOP]
+
+        voc = _AsDecode()
+    else:
+        voc = Vocos()
+        voc.load_state_dict(vsd, strict=True)
+        voc = voc.to(dev).eval()
     del sd, vsd, sd_all
 
     cond_h, text_h = wl.cond.pin_memory(), wl.text.pin_memory()
@@ -601,9 +617,10 @@ def run_b200(args):
         "config": {"workload": wl.describe(),
                    "padded_rows": ("skipped beyond the influence cone of the position-embedding convolutions (valid rows "
                                    "unchanged, tests/test_fullnfe_gpu.py)" if model.skip_padded_rows else "computed"),
-                   "weights": "full 336M-parameter DiT (22 layers) + Vocos, seeded random init (no checkpoints offline)",
+                   "weights": "full 336M-parameter DiT (22 layers) + " + ("BigVGAN-v2 (112M)" if args.vocoder == "bigvgan" else "Vocos")
+                              + ", seeded random init (no checkpoints offline)",
                    "step": f"CFM.sample ({variants * cfg.steps} co-batched DiT forwards, graph-replayed ODE steps) + "
-                           "Vocos.decode of one utterance batch per GPU",
+                           + ("BigVGAN" if args.vocoder == "bigvgan" else "Vocos.decode") + " of one utterance batch per GPU",
                    "l2": "256 MiB buffer written between timed iterations; per-step working set (0.7 GB weights) > L2",
                    "parallelism": f"utterance sharding x{world}, one weight broadcast, no per-step collective"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
