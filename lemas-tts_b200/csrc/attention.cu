@@ -466,11 +466,11 @@ extern "C" int lemas_attention_f16(const void* qk, int32_t ld_qk, const void* vt
   // (attention9.cu: one 64-key pipeline per CTA, four CTAs per SM — twice the blocks per CTA, no merge: C4's 768 keys
   // 229 vs 238 us, the ragged C3 mix 227 vs 246 us); long uniform sequences stay on v3 (C2 59.5 vs 60.2 us, C5 88 vs 100:
   // v9's 592 CTA slots quantise 704 tiles into two waves).  profiles/r02ah_attention_v9.log
-  // v9 needs enough tiles to fill its 4 x 148 CTA slots about twice: with few tiles (one short utterance: 2 x 1024 keys,
+  // v9 needs enough tiles to fill its 4 x 148 CTA slots more than once: with few tiles (one short utterance: 2 x 1024 keys,
   // 256 tiles) v3's two pipelines per tile finish in 16 us where v9's single one needs 28.
   if (variant == kAutoVariant) {
     const long tiles = (long)((seq + 127) / 128) * heads * batch;
-    variant = ((kv_len != nullptr || seq <= 1024) && tiles >= 8L * sm_count()) ? 40 : 0;
+    variant = ((kv_len != nullptr || seq <= 1024) && tiles >= 5L * sm_count()) ? 40 : 0;   // crossover measured at ~750 tiles
   }
   if (variant < 7)
     return attention_v3_launch(qk, ld_qk, vt, vt_ld, kv_len, out16, batch, seq, heads, g_att_trace, stream);
