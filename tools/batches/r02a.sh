@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch A: attention v5 parity + variant timings, full-NFE goldens, regression of the GPU suite, C2 bench.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 nvidia-smi -L > $O/r02a_gpu.txt 2>&1
 echo "== attention tests (v5 default)" | tee $O/r02a_att.log

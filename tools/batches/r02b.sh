@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch B: attention v5 scheduling experiments (control-warp position, pipeline stagger) + traces.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 L=$O/r02b_bench_att.log; : > $L
 for cfg in "600 300" "0 0" "1000 500" "1300 650" "500 1000"; do

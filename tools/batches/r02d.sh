@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch D: attention v6 (double-buffered scores) parity, timings, trace.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 L=$O/r02d_bench_att.log; : > $L
 for v in 5 4 6; do

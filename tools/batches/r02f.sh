@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch F: attention v7 (four key parts, double-buffered scores) parity, timings, trace.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 L=$O/r02f_bench_att.log; : > $L
 for v in 8 7 9; do

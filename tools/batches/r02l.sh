@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch L: bench with in-graph kernel timing, ncu launch list with graph-node profiling, sanitizers
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 900 python bench.py --steps 5 --warmup 3 > $O/r02l_bench_C2.json 2> $O/r02l_bench_C2.err; python - <<'PY'
 import json

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 900 python bench.py --steps 5 --warmup 3 --no-c4 > $O/r02m_bench_C2.json 2> $O/r02m_bench_C2.err; python - <<'PY'
 import json

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU batch O: folded LayerNorm — parity of the whole suite, C2 bench with and without
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -q -x -s > $O/r02o_tests.txt 2>&1; grep -E "full_C|passed|failed|Error|assert" $O/r02o_tests.txt | tail -12
 for f in 1 0; do
