@@ -1,4 +1,6 @@
-"""GPU parity of the tcgen05 attention kernel (csrc/attention.cu) through the C ABI.
+"""GPU parity of the tcgen05 attention kernels through the C ABI: csrc/attention.cu (v3: long uniform sequences) and
+csrc/attention9.cu (v9: batches of short or ragged sequences); `lemas_attention_f16` chooses by shape, the tests force
+each kernel on every shape.
 
 Checker: fp32 softmax(QK^T/8 + keymask)V in PyTorch on the same fp16 q/k/v.  P is rounded to fp16 before the PV
 MMA, so the bar is 4e-3 absolute on outputs of magnitude O(1) (documented in DESIGN.md).
@@ -20,9 +22,21 @@ def _ref(q, k, v, kv_len):
     return s.softmax(-1) @ v.float()
 
 
+@pytest.fixture(params=[0, 40, 100], ids=["v3", "v9", "auto"])
+def kernel_variant(request):
+    """Force one production kernel (0 = v3, 40 = v9) or leave the choice to the library (100)."""
+    from lemas_tts import _native as nv
+
+    lib = nv.load()
+    lib.lemas_debug_attention_variant(request.param)
+    yield request.param
+    lib.lemas_debug_attention_variant(100)
+
+
 @pytest.mark.parametrize("B,N,H,ragged", [(1, 97, 4, False), (1, 128, 2, False), (2, 300, 4, True),
-                                           (1, 2187, 16, False), (3, 640, 2, True), (2, 129, 1, True)])
-def test_attention_matches_fp32(B, N, H, ragged):
+                                           (1, 2187, 16, False), (3, 640, 2, True), (2, 129, 1, True),
+                                           (64, 300, 16, True)])
+def test_attention_matches_fp32(B, N, H, ragged, kernel_variant):
     from lemas_tts import ops
 
     g = torch.Generator().manual_seed(N + H)
@@ -31,7 +45,7 @@ def test_attention_matches_fp32(B, N, H, ragged):
     v = torch.randn(B, H, N, 64, generator=g).cuda().half()
     kv_len = None
     if ragged:
-        kv_len = torch.tensor([N, max(1, N // 3), 5][:B], device="cuda", dtype=torch.int32)
+        kv_len = torch.tensor(([N, max(1, N // 3), 5] * ((B + 2) // 3))[:B], device="cuda", dtype=torch.int32)
     inner = H * 64
     qk = torch.cat((q.transpose(1, 2).reshape(B * N, inner), k.transpose(1, 2).reshape(B * N, inner)), dim=1).contiguous()
     npad = (N + 63) // 64 * 64
@@ -49,7 +63,7 @@ def test_attention_matches_fp32(B, N, H, ragged):
 
 
 @pytest.mark.timeout(120)
-def test_attention_multiwave_back_to_back_launches():
+def test_attention_multiwave_back_to_back_launches(kernel_variant):
     """Regression (round 1): 2 x 16 x 18 = 576 CTAs (two waves on 148 SMs x 2) launched back to back, last query tile
     with three all-padding warps per key half.  Their lanes polled the barrier independently, lane 0 ran ahead and the
     parity wait of the others was lapped -> the kernel hung.  Must finish, and every launch must give the same bits."""
