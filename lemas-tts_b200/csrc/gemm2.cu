@@ -237,7 +237,10 @@ DEVI bool tile_skipped(const GemmParams& p, int batch_item, int first_row) {
   return p.row_limit != nullptr && first_row >= __ldg(p.row_limit + batch_item);
 }
 
-template <int EPI, bool FOLD>
+// BN = 256: the production tile.  BN = 128 (256 x 128 pair tiles, same shared-memory layout, half the B bytes per
+// stage): chosen by gemm2_launch when the 256-wide tiling would leave more than half of the CTA pairs idle (small M:
+// one short utterance) — twice the tiles, half the serial MMA chain per tile.
+template <int EPI, bool FOLD, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
              const __grid_constant__ GemmParams p) {
@@ -255,7 +258,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int pair = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int m_tiles_b = (p.rows + 2 * G2_BM - 1) / (2 * G2_BM);  // per batch item: tiles never straddle items
-  const int n_tiles = p.n / G2_BN;
+  const int n_tiles = p.n / BN;
   const int num_tiles = p.batches * m_tiles_b * n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -289,10 +292,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int bi = mt / m_tiles_b;
         if (tile_skipped(p, bi, (mt - bi * m_tiles_b) * (2 * G2_BM))) continue;
         const int m0 = (mt - bi * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM;
-        const int n0 = n_idx * G2_BN + (int)rank * (G2_BN / 2);
+        const int n0 = n_idx * BN + (int)rank * (BN / 2);
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * G2_STAGE_BYTES);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (G2_A_BYTES + (BN / 2) * G2_BK * 2));
           const uint32_t full_leader = mapa_shared(smem_u32(full_bar + stage), 0);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
           tma_load_3d_pair(sa, &tmA, full_leader, it * G2_BK, m0, bi);
@@ -303,7 +306,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(2 * G2_BM, G2_BN);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * G2_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -315,7 +318,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         mbar_wait_cluster(acc_empty + acc, acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
@@ -351,7 +354,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       rc.pos0 = (mt - rc.b * m_tiles_b) * (2 * G2_BM) + (int)rank * G2_BM + sub * 32;
       rc.nrows = min(32, p.rows - rc.pos0);
       rc.grow0 = (long)rc.b * p.rows + rc.pos0;
-      const int n0 = n_idx * G2_BN;
+      const int n0 = n_idx * BN;
       // Per-column vectors (bias, gate) for this thread's 4 columns of each 32-column block are fetched one block
       // ahead; block 0's are issued before the accumulator wait so their latency hides behind the main loop.
       // The block loop stays rolled: these kernels run a few microseconds, every instruction executes only a
@@ -365,9 +368,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (p.gate != nullptr && p.gate_bstride == 0) return __ldg(reinterpret_cast<const float4*>(p.gate + ccol + j * 32));
         return make_float4(1.f, 1.f, 1.f, 1.f);
       };
-      const int j0 = half * 4;
+      static_assert(!FOLD || BN == 256, "the folded LayerNorm is built for 256-column tiles");
+      constexpr int NB = BN / 64;   // 32-column blocks per epilogue warp (the warp owns half of the tile's columns)
+      const int j0 = half * NB;
       float4 bias_nxt = load_bias(j0), gate_nxt = load_gate(j0);
-      const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + acc * G2_BN;
+      const uint32_t t_addr = tmem_base + (uint32_t(sub * 32) << 16) + acc * BN;
       if (rc.nrows > 0) {
         float4 pre_nxt[8];
         epi2_prefetch<EPI>(p, rc, n0 + j0 * 32, lane, pre_nxt);  // does not depend on the accumulator either
@@ -430,12 +435,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(acc_full + acc, acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = j0; j < j0 + 4; ++j) {
+        for (int j = j0; j < j0 + NB; ++j) {
           const float4 bias4 = bias_nxt, gate4 = gate_nxt, lnu4 = lnu_nxt, lnv4 = lnv_nxt;
           float4 pre[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) pre[i] = pre_nxt[i];
-          if (j < j0 + 3) {
+          if (j < j0 + NB - 1) {
             bias_nxt = load_bias(j + 1);
             gate_nxt = load_gate(j + 1);
             if constexpr (FOLD) { lnu_nxt = load_lnu(j + 1); lnv_nxt = load_lnv(j + 1); }
@@ -468,18 +473,41 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
-template <int EPI, bool FOLD = false>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st) {
+template <int EPI, bool FOLD, int BN>
+static int launch2_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st) {
   static unsigned long long configured = 0;
-  auto kern = gemm2_kernel<EPI, FOLD>;
+  auto kern = gemm2_kernel<EPI, FOLD, BN>;
   LEMAS_CUDA_OK(ensure_dynamic_smem(kern, G2_SMEM, configured));
-  const int tiles = p.batches * ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / G2_BN);
+  const int tiles = p.batches * ((p.rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (p.n / BN);
   int pairs = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
   if (pairs < 1) pairs = 1;
   if (pairs > tiles) pairs = tiles;
   LEMAS_CUDA_OK(launch_pdl(kern, dim3(2 * pairs), dim3(G2_THREADS), G2_SMEM, st, tmA, tmW, p));
   LEMAS_LAUNCHED(1);
   return LEMAS_OK;
+}
+
+template <int EPI, bool FOLD = false>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int max_ctas, cudaStream_t st,
+                   int bn = 256) {
+  if constexpr (!FOLD)
+    if (bn == 128) return launch2_bn<EPI, false, 128>(tmA, tmW, p, max_ctas, st);
+  return launch2_bn<EPI, FOLD, 256>(tmA, tmW, p, max_ctas, st);
+}
+
+// 256 x 128 tiles for small problems when they need fewer (weighted) waves than 256 x 256 ones — one short utterance:
+// to_out 12.7 -> 9.2 us, FF2 17.7 -> 12.7 us, QKV 18.6 -> 16.9 us at M = 1880 (LEMAS_G2_BN = 128 | 256 forces one)
+static int pick_bn2(const lemas_gemm_desc& d, int batches, int rows, const GemmParams& p) {
+  static const int forced = [] { const char* e = getenv("LEMAS_G2_BN"); return e ? atoi(e) : 0; }();
+  if (p.ln_out16 != nullptr || p.ln_stats_in != nullptr) return 256;
+  if (forced == 128 || forced == 256) return forced;
+  const long tiles256 = (long)batches * ((rows + 2 * G2_BM - 1) / (2 * G2_BM)) * (d.n / 256);
+  const long pairs = (d.max_ctas > 0 ? d.max_ctas : sm_count()) / 2;
+  if (tiles256 > 2 * pairs) return 256;   // large problems: the wider tile moves fewer operand bytes (measured at M = 4374)
+  // small problems are a handful of waves: a 256 x 128 tile costs ~0.62 of a 256 x 256 one (measured, M = 1880)
+  const double cost256 = (double)((tiles256 + pairs - 1) / pairs);
+  const double cost128 = 0.62 * (double)((2 * tiles256 + pairs - 1) / pairs);
+  return cost128 < cost256 ? 128 : 256;
 }
 
 bool gemm2_eligible(const lemas_gemm_desc& d) {
@@ -503,6 +531,7 @@ int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p_in, cudaStream_t 
   GemmParams p = p_in;
   p.batches = batches;
   p.rows = rows;
+  const int bn = pick_bn2(d, batches, rows, p);
   CUtensorMap tmA, tmW;
   {
     uint64_t dims[3] = {(uint64_t)d.a_cols, (uint64_t)rows, (uint64_t)batches};
@@ -513,22 +542,22 @@ int gemm2_launch(const lemas_gemm_desc& d, const GemmParams& p_in, cudaStream_t 
   {
     uint64_t dims[2] = {(uint64_t)d.ldw, (uint64_t)d.w_rows};
     uint64_t strides[1] = {(uint64_t)d.ldw * 2};
-    uint32_t box[2] = {G2_BK, G2_BN / 2};
+    uint32_t box[2] = {G2_BK, (uint32_t)(bn / 2)};
     LEMAS_TRY(make_tensor_map_f16(&tmW, d.w, 2, dims, strides, box));
   }
   switch (d.epilogue) {
-    case LEMAS_EPI_BIAS_F16: return launch2<LEMAS_EPI_BIAS_F16>(tmA, tmW, p, d.max_ctas, st);
+    case LEMAS_EPI_BIAS_F16: return launch2<LEMAS_EPI_BIAS_F16>(tmA, tmW, p, d.max_ctas, st, bn);
     case LEMAS_EPI_QKV_ROPE:
       return p.ln_stats_in ? launch2<LEMAS_EPI_QKV_ROPE, true>(tmA, tmW, p, d.max_ctas, st)
-                           : launch2<LEMAS_EPI_QKV_ROPE>(tmA, tmW, p, d.max_ctas, st);
+                           : launch2<LEMAS_EPI_QKV_ROPE>(tmA, tmW, p, d.max_ctas, st, bn);
     case LEMAS_EPI_GELU_TANH_F16:
       return p.ln_stats_in ? launch2<LEMAS_EPI_GELU_TANH_F16, true>(tmA, tmW, p, d.max_ctas, st)
-                           : launch2<LEMAS_EPI_GELU_TANH_F16>(tmA, tmW, p, d.max_ctas, st);
-    case LEMAS_EPI_GELU_ERF_F16: return launch2<LEMAS_EPI_GELU_ERF_F16>(tmA, tmW, p, d.max_ctas, st);
+                           : launch2<LEMAS_EPI_GELU_TANH_F16>(tmA, tmW, p, d.max_ctas, st, bn);
+    case LEMAS_EPI_GELU_ERF_F16: return launch2<LEMAS_EPI_GELU_ERF_F16>(tmA, tmW, p, d.max_ctas, st, bn);
     case LEMAS_EPI_GATE_RESID_F32:
       return p.ln_out16 ? launch2<LEMAS_EPI_GATE_RESID_F32, true>(tmA, tmW, p, d.max_ctas, st)
-                        : launch2<LEMAS_EPI_GATE_RESID_F32>(tmA, tmW, p, d.max_ctas, st);
-    case LEMAS_EPI_BIAS_F32: return launch2<LEMAS_EPI_BIAS_F32>(tmA, tmW, p, d.max_ctas, st);
+                        : launch2<LEMAS_EPI_GATE_RESID_F32>(tmA, tmW, p, d.max_ctas, st, bn);
+    case LEMAS_EPI_BIAS_F32: return launch2<LEMAS_EPI_BIAS_F32>(tmA, tmW, p, d.max_ctas, st, bn);
   }
   return fail(LEMAS_ERR_INVALID, "gemm2: unsupported epilogue");
 }
